@@ -1,0 +1,177 @@
+#!/usr/bin/env python
+"""Generate tests/golden/* by running the UNMODIFIED reference in this container.
+
+TEST INFRASTRUCTURE ONLY. Needs /root/reference (absent on the GPU box - the fixtures it
+writes are committed so nothing at test time reads the reference tree).
+
+    python oracle/make_golden.py
+
+Imports, through oracle/ref_shims (ftfy = identity, nltk/torchmetrics stubs):
+  * utils_attacks.generate_sentence / attack_text_leaf      (/root/reference/utils_attacks.py)
+  * open_clip.tokenizer.SimpleTokenizer                     (/root/reference/src/open_clip/tokenizer.py)
+  * open_clip.model.CLIP.encode_text                        (/root/reference/src/open_clip/model.py)
+"""
+import json
+import os
+import random
+import string
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+REF = os.environ.get("LEAF_REFERENCE", "/root/reference")
+sys.path[:0] = [os.path.join(HERE, "ref_shims"), os.path.join(REF, "src"), REF, ROOT]
+
+import open_clip  # noqa: E402
+import utils_attacks  # noqa: E402
+from open_clip.model import CLIP, CLIPTextCfg, CLIPVisionCfg  # noqa: E402
+
+from leaf_b200 import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+V = synth.V_DEFAULT
+
+
+def gen_edit():
+    rng = random.Random(7)
+    strings = ["", "a", "ab", "a b", "hello world", "a_b", "  x ", "Cat's", "&lt", "zz top!"]
+    for _ in range(10):
+        n = rng.randint(3, 14)
+        strings.append("".join(rng.choice(string.ascii_letters + "  _&;'") for _ in range(n)))
+    chars = [0, 27, 1, 2, 28, 53, 60, 70, 95] + [V.index(ord(c)) for c in "_&;' "]
+    cases = []
+    for S in strings:
+        for z in range(2 * len(S) + 1):
+            us = set(chars)
+            if z % 2 == 1 and ord(S[z // 2]) in V:
+                us.add(V.index(ord(S[z // 2])))       # "same character" => delete
+            for u in sorted(us):
+                out = utils_attacks.generate_sentence(S, z, u, V, 1, alternative=-1)
+                cases.append([S, z, V[u], out])
+    # the phase-1 form: generate_all_sentences(S, [ord(' ')], subset_z, alternative=-1)
+    probe = []
+    for S in strings[:12]:
+        zs = list(range(2 * len(S) + 1))
+        probe.append([S, zs, utils_attacks.generate_all_sentences(S, [ord(" ")], subset_z=zs, alternative=-1)])
+    json.dump({"V": V, "cases": cases, "probe": probe}, open(os.path.join(OUT, "edit_golden.json"), "w"))
+    print("edit cases", len(cases))
+
+
+APPENDIX_B = [
+    "a photo of a cat", "it's", "dogs'street", "a!!'s", "3d 42", "a_b", "x <start_of_text> y", "&amp;",
+    "a &#65; b", "x&ltb", "cats &not here", "AT&T center &cent", "  Hello   WORLD  ", "e.g. a cat.",
+    "don't'll", "#$%&'()*+", "a\tb\nc", "a" * 90, "a" * 90 + " " + "zq " * 80,
+    "&not &notit; &lt &amp;lt; &#x41 &#65 &#0; &#128; &copy", "", " ", "&", "&;", "&#", "&#;", "&#x;", "&#xg",
+    "<end_of_text>", "a<end_of_text>b", "!<start_of_text>", "<START_OF_TEXT>", "&amplt", "&ampamp;lt",
+    "&nbsp", "a&nbspb", "&#9;x", "a&#32;b", "&#10", "&shy", "x&shyy", "&micro", "&MICRO", "&Aacute", "&aacute",
+    "&AMP", "&QUOT", "&quot", "&THORN", "&eth", "&ETH", "&times", "&divide", "&frac12", "&sup2", "1&frac123",
+    "&#255", "&#256", "&#xff;", "&#XFF", "&#x100", "&#65x", "&#0065", "&#1 dad", "&#128", "&#150;", "&#x9f",
+    "&lambda;", "&Lambda;", "&hellip;", "&notin;", "&notin", "&lt;&gt;", "&lt&gt", "a&b", "a & b", "&&lt",
+    "&#38;lt;", "&#38lt", "&amp;#65;", "&ordf", "&ordm", "&szlig", "&yuml", "&sup1&sup3", "&para&sect",
+    "'S", "'RE", "A'LL b'D", "''s", "'s's", "x'", "'", "1'2", "a1b2", "12ab", "a.b", "...", "a - b",
+    "don’t", "\x1c", "a\x1cb", "a\x85b", "a\xa0b", "\x0b\x0c",
+]
+
+
+def gen_tokenizer():
+    tok = open_clip.get_tokenizer("ViT-L-14")
+    rng = random.Random(11)
+    texts = list(APPENDIX_B)
+    alpha = string.ascii_lowercase * 3 + string.ascii_uppercase + string.digits + "   '&;<_#x" + string.punctuation
+    frags = ["&lt", "&gt", "&amp", "&not", "&copy", "&reg", "&deg", "&cent", "&nbsp", "&#", "&#x", "'s", "'t",
+             "'re", "'ve", "'m", "'ll", "'d", "<start_of_text>", "<end_of_text>", ";", "&quot", "&yen", "&uml",
+             "&para", "&sect", "&shy", "&eth", "&times", "&micro", "&frac12", "&Aacute", "&ntilde", "&#65", "&#x41"]
+    for _ in range(2600):
+        n = rng.randint(1, 70)
+        s = "".join(rng.choice(alpha) for _ in range(n))
+        for _ in range(rng.randint(0, 3)):
+            p = rng.randint(0, len(s))
+            s = s[:p] + rng.choice(frags) + s[p:]
+        texts.append(s)
+    # attack-shaped strings: synthetic captions with one edit from V
+    caps = synth.make_captions(24, seed=3, kind="typical") + synth.make_captions(4, seed=3, kind="dense-77")
+    for S in caps:
+        for _ in range(12):
+            z = rng.randint(0, 2 * len(S))
+            u = rng.randrange(len(V))
+            texts.append(utils_attacks.generate_sentence(S, z, u, V, 1, alternative=-1))
+    enc = [[t, tok.encode(t)] for t in texts]
+    rows_in = ["a photo of a cat", "a" * 90 + " " + "zq " * 80, "", caps[-1], caps[0], "x <end_of_text> y"]
+    rows = tok(rows_in).tolist()
+    json.dump({"encode": enc, "rows_in": rows_in, "rows": rows},
+              open(os.path.join(OUT, "tokenizer_golden.json"), "w"))
+    print("tokenizer strings", len(enc))
+
+
+def build_ref_clip(cfg: synth.TowerCfg, sd):
+    model = CLIP(embed_dim=cfg.embed_dim,
+                 vision_cfg=CLIPVisionCfg(layers=1, width=64, head_width=32, patch_size=16, image_size=32),
+                 text_cfg=CLIPTextCfg(context_length=cfg.context_length, vocab_size=cfg.vocab_size,
+                                      width=cfg.width, heads=cfg.heads, layers=cfg.layers),
+                 quick_gelu=cfg.quick_gelu)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(m.startswith("visual.") or m in ("logit_scale",) for m in missing), missing
+    return model.eval()
+
+
+def gen_tower():
+    tok = open_clip.get_tokenizer("ViT-L-14")
+    caps = synth.make_captions(10, seed=5, kind="typical") + synth.make_captions(2, seed=5, kind="dense-77") \
+        + ["", "a", "x <end_of_text> y z"]
+    tokens = tok(caps)
+    out = {"tokens": tokens.numpy()}
+    for name, quick in (("tiny", False), ("tiny", True), ("small", False)):
+        cfg = synth.TOWERS[name]
+        cfg = synth.TowerCfg(cfg.name, cfg.width, cfg.layers, cfg.heads, cfg.embed_dim, quick_gelu=quick)
+        sd = synth.random_tower_state_dict(cfg, seed=21, exact_numpy=True)
+        model = build_ref_clip(cfg, sd)
+        with torch.no_grad():
+            f = model.encode_text(tokens, normalize=False)
+            fn = model.encode_text(tokens, normalize=True)
+        tag = f"{name}_{'quick' if quick else 'gelu'}"
+        out[tag] = f.numpy()
+        out[tag + "_norm"] = fn.numpy()
+    np.savez_compressed(os.path.join(OUT, "tower_golden.npz"), **out)
+    json.dump({"captions": caps}, open(os.path.join(OUT, "tower_golden.json"), "w"))
+    print("tower fixtures", {k: v.shape for k, v in out.items()})
+
+
+def gen_attack():
+    tok = open_clip.get_tokenizer("ViT-L-14")
+    cfg = synth.TOWERS["tiny"]
+    sd = synth.random_tower_state_dict(cfg, seed=31, exact_numpy=True)
+    sd_frozen = synth.perturbed_copy(sd, seed=32, std=1e-2, exact_numpy=True)
+    model = build_ref_clip(cfg, sd)
+    frozen = build_ref_clip(cfg, sd_frozen)
+    cases = []
+    arrays = {}
+    for ci, (B, n, k, seed, kind, objective) in enumerate([
+            (6, 10, 1, 0, "typical", "l2"), (6, 50, 1, 1, "typical", "l2"), (4, 120, 1, 2, "short", "l2"),
+            (5, 20, 2, 3, "typical", "l2"), (3, 16, 3, 4, "short", "l2"), (2, 30, 1, 5, "dense-77", "l2"),
+            (1, 24, 1, 6, "typical", "sim"), (1, 24, 1, 7, "typical", "dissim"), (4, 24, 1, 8, "typical", "negl2")]):
+        caps = synth.make_captions(B, seed=100 + seed, kind=kind)
+        with torch.no_grad():
+            anchor = frozen.encode_text(tok(caps), normalize=objective in ("sim", "dissim"))
+            np.random.seed(seed)
+            feats, adv = utils_attacks.attack_text_leaf(model, tok, caps, anchor.clone(), "cpu", objective=objective,
+                                                        n=n, k=k, V=V, constrain=False)
+        cases.append(dict(B=B, n=n, k=k, seed=seed, kind=kind, objective=objective, captions=caps, adv=adv))
+        arrays[f"anchor_{ci}"] = anchor.numpy()
+        arrays[f"feats_{ci}"] = feats.numpy()
+    json.dump({"tower": "tiny", "seed": 31, "frozen_seed": 32, "frozen_std": 1e-2, "cases": cases},
+              open(os.path.join(OUT, "attack_golden.json"), "w"))
+    np.savez_compressed(os.path.join(OUT, "attack_golden.npz"), **arrays)
+    print("attack cases", len(cases))
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    gen_edit()
+    gen_tokenizer()
+    gen_tower()
+    gen_attack()
