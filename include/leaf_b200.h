@@ -1,0 +1,147 @@
+/*
+ * leaf_b200.h - C ABI of the B200-native engine for LEAF's inner attack loop.
+ *
+ * The reference (LIONS-EPFL/LEAF) has no FFI layer: its seam is the Python call
+ *   attack_text_leaf(model, tokenizer, sentences, anchor_features, device, objective, n, k, V, constrain)
+ *   (utils_attacks.py:297-393) plus model.encode_text (src/open_clip/model.py:269-284) and
+ *   tokenizer(list[str]) (src/open_clip/tokenizer.py:226-265).
+ * Every entry point below states which reference lines it replaces. The Python mirror of the
+ * reference interface (leaf_b200/attack.py) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns LEAF_OK (0) or a negative leaf_status_t; nothing throws across the ABI;
+ *     leaf_last_error() returns a thread-local UTF-8 message for the last failure;
+ *   - all tensor pointers are DEVICE pointers owned by the caller (PyTorch); the engine owns only
+ *     its workspace and its bf16 weight copies; int32 unless stated otherwise;
+ *   - work is enqueued on the given cudaStream_t (passed as void*) and is asynchronous;
+ *   - one handle per (device, stream user); a handle is not thread-safe;
+ *   - there is no CPU path: every call fails with LEAF_ERR_CUDA when no sm_100 device is present.
+ */
+#ifndef LEAF_B200_H_
+#define LEAF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  LEAF_OK = 0,
+  LEAF_ERR_INVALID = -1,      /* bad argument / shape */
+  LEAF_ERR_CUDA = -2,         /* CUDA runtime or driver failure, or no sm_100 device */
+  LEAF_ERR_STATE = -3,        /* call order (weights not bound, tables not loaded, workspace too small) */
+  LEAF_ERR_UNSUPPORTED = -4   /* input outside the tokenizer's closed domain (see leaf_tokenize_status) */
+} leaf_status_t;
+
+typedef struct leaf_engine* leaf_handle_t;
+
+enum { LEAF_ACT_GELU_ERF = 0, LEAF_ACT_QUICK_GELU = 1 };
+enum { LEAF_OBJ_L2 = 0, LEAF_OBJ_NEGL2 = 1, LEAF_OBJ_SIM = 2, LEAF_OBJ_DISSIM = 3 };
+enum { LEAF_CTX = 77, LEAF_SOT = 49406, LEAF_EOT = 49407, LEAF_VOCAB = 49408, LEAF_N_MERGES = 48894 };
+enum { LEAF_MAX_CAPTION_BYTES = 1000 };
+
+/* Text-tower shape: src/open_clip/model_configs/ViT-{L,H,g,bigG}-14.json "text_cfg" + "embed_dim". */
+typedef struct {
+  int32_t width;        /* W, multiple of 128 */
+  int32_t layers;       /* L */
+  int32_t heads;        /* H, head_dim = W / H must be 64 */
+  int32_t embed_dim;    /* E */
+  int32_t activation;   /* LEAF_ACT_* : nn.GELU (model.py:192) or QuickGELU (transformer.py:33-36) */
+  float ln_eps;         /* 1e-5, torch default used by transformer.py:24-30 */
+} leaf_cfg_t;
+
+/* Per-layer fp32 parameter pointers, open_clip layout (transformer.py:210-252).
+ * For the HF CLIPTextModel layout the host wrapper passes q/k/v separately (in_proj_* == NULL). */
+typedef struct {
+  const float* ln1_w; const float* ln1_b;
+  const float* in_proj_w;  /* [3W, W] rows q;k;v, or NULL when q_w/k_w/v_w are given */
+  const float* in_proj_b;  /* [3W] */
+  const float* q_w; const float* k_w; const float* v_w;   /* [W, W] each (HF layout) */
+  const float* q_b; const float* k_b; const float* v_b;   /* [W] each */
+  const float* out_w; const float* out_b;                 /* [W, W], [W] */
+  const float* ln2_w; const float* ln2_b;
+  const float* fc1_w; const float* fc1_b;                 /* [4W, W], [4W] */
+  const float* fc2_w; const float* fc2_b;                 /* [W, 4W], [W] */
+} leaf_layer_ptrs_t;
+
+typedef struct {
+  const float* token_embedding;       /* [49408, W]   model.py:272 */
+  const float* positional_embedding;  /* [77, W]      model.py:274 */
+  const float* lnf_w; const float* lnf_b;   /* ln_final, model.py:279 */
+  const float* text_projection;       /* open_clip: [W, E] used as x @ P (model.py:282); HF: [E, W] */
+  int32_t projection_is_ew;           /* 0 = [W, E] (open_clip), 1 = [E, W] (HF text_projection.weight) */
+  const leaf_layer_ptrs_t* layers;    /* [L] host array */
+} leaf_weight_ptrs_t;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out);
+int leaf_destroy(leaf_handle_t h);
+const char* leaf_last_error(void);
+const char* leaf_version(void);
+
+/* CLIP BPE merge table: merge_pairs[r] = (left_id << 16) | right_id for rank r, merged id = 512 + r
+ * (what SimpleTokenizer.__init__ builds from bpe_simple_vocab_16e6.txt.gz, tokenizer.py:142-158).
+ * HOST pointer; copied into a device hash table. */
+int leaf_load_bpe(leaf_handle_t h, const uint32_t* merge_pairs_host, int32_t n_merges);
+
+/* Bind the live fp32 parameters (device pointers stay owned by torch) and make the engine's bf16
+ * operand copies. leaf_refresh_weights re-casts after each optimizer step (the attacked tower is the
+ * trained tower, utils_AT.py:307 vs :339-362). */
+int leaf_bind_weights(leaf_handle_t h, const leaf_weight_ptrs_t* w, void* stream);
+int leaf_refresh_weights(leaf_handle_t h, void* stream);
+
+/* Workspace for up to max_seqs token rows per call (worst case 77 positions each). */
+int leaf_reserve(leaf_handle_t h, int32_t max_seqs);
+
+/* ---- K1: candidate expansion + CLIP tokenization ---------------------------------------------
+ * Replaces generate_all_sentences / generate_random_sentences_at_z (utils_attacks.py:215-236,
+ * 275-295, called at :318 and :357), the constraint substitution (:321-325, :360-364) and
+ * tokenizer(SS) (:327, :366 -> tokenizer.py:226-265).
+ *   caps/cap_off : B captions, concatenated bytes and [B+1] offsets (ASCII, each <= LEAF_MAX_CAPTION_BYTES)
+ *   pos  [B,n]   : edit position z in [0, 2*len] per candidate; if sel != NULL the position of every
+ *                  candidate of sample b is pos[b*n + sel[b]] (phase 2: best position of phase 1, :350-353)
+ *   chr  [B,n]   : code point to write, -1 = delete (V[u], train_AT_text_only.py:93)
+ *   valid[B,n]   : 0 => candidate is replaced by the unedited caption (:325); NULL = all valid
+ *   n == 0       : tokenize the B captions themselves (tokenizer(texts), utils_AT.py:296,312)
+ *   tok_out [R,77] int32 zero padded, R = B*max(n,1); len_out[R] = argmax(ids)+1 (transformer.py:661)
+ * Token ids equal SimpleTokenizer's bit for bit. status_out (device int32[1], may be NULL) gets
+ * OR-ed flags: 1 = an html entity expanded outside U+0000..U+00FF, 2 = non-ASCII caption byte. */
+int leaf_expand_tokenize(leaf_handle_t h, const uint8_t* caps, const int32_t* cap_off, int32_t B, int32_t n,
+                         const int32_t* pos, const int32_t* chr, const int32_t* sel, const uint8_t* valid,
+                         int32_t* tok_out, int32_t* len_out, int32_t* status_out, void* stream);
+
+/* ---- K2: text tower forward -------------------------------------------------------------------
+ * Replaces CLIP.encode_text(tokens, normalize) (model.py:269-284; transformer.py:254-265,355-366,
+ * 653-665). tok [N,77] int32, len [N] (positions after argmax(ids) are dead under the causal mask and
+ * are not computed). feat_out [N,E] fp32. bf16 tensor-core GEMMs, fp32 accumulate/residual/LN/softmax. */
+int leaf_encode(leaf_handle_t h, const int32_t* tok, const int32_t* len, int32_t N, int32_t normalize,
+                float* feat_out, void* stream);
+
+/* ---- K3: TextFARE score + per-sample argmax ----------------------------------------------------
+ * Replaces utils_attacks.py:332-348 / :370-386 / :393. feat [B*n,E] fp32, anchor [B,E] fp32.
+ * loss_out [B,n] (may be NULL); best_out [B] = first index of the maximum (torch.argmax);
+ * best_feat_out [B,E] (may be NULL) = features of the winner. */
+int leaf_score(leaf_handle_t h, const float* feat, const float* anchor, int32_t B, int32_t n, int32_t objective,
+               float* loss_out, int32_t* best_out, float* best_feat_out, void* stream);
+
+/* ---- test / bench hooks (used by tests/ and bench.py only) ------------------------------------ */
+/* C[M,N] = A[M,K] . Bt[N,K]^T (+bias[N]) with the tower's tcgen05 kernel. epilogue: 0 = bf16 store,
+ * 1 = bf16 store after activation `act`, 2 = fp32 C += result (residual), 3 = fp32 store.
+ * A, Bt bf16 row-major; m_dev (device int32, may be NULL) overrides M at run time. */
+int leaf_gemm_bf16(leaf_handle_t h, const void* A, const void* Bt, const float* bias, void* C,
+                   int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t act, const int32_t* m_dev,
+                   void* stream);
+/* Number of kernels the engine has launched since the last call with reset != 0. */
+int64_t leaf_launch_count(leaf_handle_t h, int32_t reset);
+/* Packed-row count of the last leaf_encode (device int32[1], asynchronous w.r.t. the host). */
+const int32_t* leaf_last_rows_dev(leaf_handle_t h);
+/* Accumulated device time (ms) of kernels in class `which` (0 = GEMM) between CUDA events, when
+ * timing was enabled with leaf_set_timing(h, 1). Synchronises the stream. */
+int leaf_set_timing(leaf_handle_t h, int32_t on);
+double leaf_timing_ms(leaf_handle_t h, int32_t which, int32_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEAF_B200_H_ */

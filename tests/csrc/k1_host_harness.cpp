@@ -1,0 +1,46 @@
+// TEST INFRASTRUCTURE ONLY - compiles the K1 scalar core (leaf_b200/csrc/k1_core.cuh) for the CPU so that the
+// `-m "not gpu"` suite can pin the integer logic of the tokenization kernel against the oracle and the
+// golden vectors generated from the reference. Never loaded by the product (leaf_b200/ has no CPU path).
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../leaf_b200/csrc/k1_tables_host.h"
+
+using namespace leaf;
+
+static std::vector<uint64_t> g_tab;
+
+extern "C" int k1h_load(const uint32_t* merge_pairs, int n) {
+  g_tab = k1_build_merge_table(merge_pairs, n);
+  return 0;
+}
+
+// same contract as leaf_expand_tokenize, host pointers; sequential emulation of "warp per candidate"
+extern "C" int k1h_expand_tokenize(const uint8_t* caps, const int32_t* cap_off, int B, int n, const int32_t* pos,
+                                   const int32_t* chr, const int32_t* sel, const uint8_t* valid, int32_t* tok_out,
+                                   int32_t* len_out) {
+  K1Tables T = k1_host_tables(g_tab.data());
+  std::vector<uint8_t> a(K1_MAX_TEXT), b(K1_MAX_TEXT);
+  std::vector<uint16_t> sym(2 * K1_MAX_TEXT), rk(2 * K1_MAX_TEXT), ps(K1_MAX_PIECES), pl(K1_MAX_PIECES);
+  K1Scratch S{a.data(), b.data(), sym.data(), rk.data(), ps.data(), pl.data(), 0, 0};
+  int flags = 0;
+  const int per = n > 0 ? n : 1;
+  for (int r = 0; r < B * per; ++r) {
+    const int bb = r / per, j = r % per;
+    const uint8_t* src = caps + cap_off[bb];
+    int len = cap_off[bb + 1] - cap_off[bb];
+    if (len > 1000) { flags |= K1_FLAG_TOO_LONG; len = 0; }
+    bool edit = n > 0 && (!valid || valid[r]);
+    int z = 0, c = -1;
+    if (n > 0) {
+      z = sel ? pos[bb * n + sel[bb]] : pos[r];
+      c = chr[r];
+    }
+    flags |= k1_prepare(T, src, len, edit, z, c, S);
+    for (int p = 0; p < S.n_pieces; ++p) k1_encode_piece(T, S, p);
+    len_out[r] = k1_emit_row(S, tok_out + (size_t)r * K1_CTX);
+  }
+  return flags;
+}

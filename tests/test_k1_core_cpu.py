@@ -1,0 +1,122 @@
+"""The K1 integer core (leaf_b200/csrc/k1_core.cuh, compiled for the CPU by tests/k1_harness.py) against the
+golden vectors generated from the reference and against the oracle. Bit-exact or fail."""
+import json
+import os
+import random
+
+import numpy as np
+
+from leaf_b200 import synth
+from oracle import leaf_oracle as O
+from tests import k1_harness as H
+
+V = synth.V_DEFAULT
+
+
+def _in_domain(text):
+    """True when both html.unescape passes stay inside U+0000..U+00FF (K1's closed domain; the check is on
+    the text BEFORE lower(), e.g. '&#x9f' -> U+0178 is outside although its lower-case U+00FF is inside)."""
+    import html
+    t1 = html.unescape(text)
+    t2 = html.unescape(t1)
+    return all(ord(c) <= 0xFF for c in t1 + t2)
+
+
+def _row(ids):
+    toks = [O.SOT] + list(ids) + [O.EOT]
+    if len(toks) > 77:
+        toks = toks[:77]
+        toks[-1] = O.EOT
+    return toks + [0] * (77 - len(toks))
+
+
+def test_golden_tokenizer_strings(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "tokenizer_golden.json")))
+    texts, want, unsup = [], [], []
+    for text, ids in g["encode"]:
+        if len(text) > 1000 or any(ord(c) > 0xFF for c in text):
+            continue
+        (texts if _in_domain(text) else unsup).append(text)
+        if texts and texts[-1] is text:
+            want.append(_row(ids))
+    assert len(texts) > 2500
+    tok, ln, flags = H.expand_tokenize(texts, encoding="latin-1")
+    want = np.array(want, dtype=np.int32)
+    bad = np.nonzero((tok != want).any(axis=1))[0]
+    assert len(bad) == 0, [(texts[i], tok[i][:12].tolist(), want[i][:12].tolist()) for i in bad[:5]]
+    assert (ln == want.argmax(axis=1) + 1).all()
+    # entity expansions that leave U+0000..U+00FF must be flagged, never silently mis-tokenized
+    for t in unsup:
+        _, _, fl = H.expand_tokenize([t], encoding="latin-1")
+        assert fl & 1, t
+    rows_in = [r for r in g["rows_in"]]
+    tok, ln, _ = H.expand_tokenize(rows_in)
+    assert tok.tolist() == g["rows"]
+
+
+def test_edit_rule_golden(golden_dir):
+    g = json.load(open(os.path.join(golden_dir, "edit_golden.json")))
+    otok = O.OracleTokenizer()
+    by_s = {}
+    for S, z, c, out in g["cases"]:
+        by_s.setdefault(S, []).append((z, c, out))
+    for S, cases in by_s.items():
+        n = len(cases)
+        tok, ln, flags = H.expand_tokenize([S], n=n, pos=[c[0] for c in cases], chr_=[c[1] for c in cases])
+        want = otok([c[2] for c in cases]).numpy()
+        assert (tok == want).all(), S
+
+
+def test_attack_shaped_candidates_vs_oracle():
+    rng = random.Random(5)
+    otok = O.OracleTokenizer()
+    for kind, B in (("typical", 24), ("dense-77", 6), ("short", 12)):
+        caps = synth.make_captions(B, seed=9, kind=kind)
+        # salt a few captions with characters that make entities / contractions / specials reachable
+        caps[0] = caps[0].replace(" ", " amp;", 1)
+        caps[1] = "it" + caps[1][:20] + " dogs'street lt;b #65; not;in"
+        caps[2] = "x start_of_text> y <end_of_text z " + caps[2]
+        n = 64
+        pos = np.array([[rng.randint(0, 2 * len(S)) for _ in range(n)] for S in caps], dtype=np.int32)
+        chr_ = np.array([[V[rng.randrange(len(V))] for _ in range(n)] for _ in caps], dtype=np.int32)
+        chr_[:, :8] = [ord(c) for c in "&<'_; #x"]
+        valid = np.ones((B, n), dtype=np.uint8)
+        valid[:, 5::7] = 0
+        # phase-1 form
+        tok, ln, flags = H.expand_tokenize(caps, n=n, pos=pos, chr_=chr_, valid=valid)
+        strings = [O.edit_sentence(S, int(pos[b, j]), int(chr_[b, j])) if valid[b, j] else S
+                   for b, S in enumerate(caps) for j in range(n)]
+        want = otok(strings).numpy()
+        ok = np.array([_in_domain(s) for s in strings])
+        assert ok.mean() > 0.95
+        assert (tok[ok] == want[ok]).all()
+        assert (ln[ok] == want[ok].argmax(axis=1) + 1).all()
+        # phase-2 form: one position per sample selected on the device side
+        sel = np.array([rng.randrange(n) for _ in caps], dtype=np.int32)
+        tok, ln, flags = H.expand_tokenize(caps, n=n, pos=pos, chr_=chr_, sel=sel)
+        strings = [O.edit_sentence(S, int(pos[b, sel[b]]), int(chr_[b, j])) for b, S in enumerate(caps) for j in range(n)]
+        want = otok(strings).numpy()
+        ok = np.array([_in_domain(s) for s in strings])
+        assert (tok[ok] == want[ok]).all()
+
+
+def test_random_fuzz_vs_oracle():
+    rng = random.Random(17)
+    otok = O.OracleTokenizer()
+    alpha = "abcdefghijklmnopqrstuvwxyz" * 2 + "ABCXYZ0123456789" + "    ''&&;;<>_#xX.,!?-" + '"$%()*+/:=@[\\]^`{|}~'
+    frags = ["&lt", "&gt;", "&amp", "&not", "&copy", "&nbsp", "&#", "&#x", "&#65", "&#x41;", "'s", "'re", "'ll",
+             "<start_of_text>", "<end_of_text>", "&amp;lt;", "&ampamp;", "&shy", "&micro", "&frac12", "&#32;", "&#9"]
+    texts = []
+    for _ in range(4000):
+        s = "".join(rng.choice(alpha) for _ in range(rng.randint(0, 60)))
+        for _ in range(rng.randint(0, 3)):
+            p = rng.randint(0, len(s))
+            s = s[:p] + rng.choice(frags) + s[p:]
+        texts.append(s)
+    texts += ["a" * 1000, "a1" * 500, ("&lt" * 300)[:1000], " " * 1000, "&" * 1000, "'" * 999 + "s"]
+    tok, ln, flags = H.expand_tokenize(texts)
+    want = otok(texts).numpy()
+    ok = np.array([_in_domain(s) for s in texts])
+    assert ok.mean() > 0.9
+    bad = np.nonzero((tok != want).any(axis=1) & ok)[0]
+    assert len(bad) == 0, [(texts[i], tok[i][:10].tolist(), want[i][:10].tolist()) for i in bad[:5]]
