@@ -132,10 +132,15 @@ int leaf_score(leaf_handle_t h, const float* feat, const float* anchor, int32_t 
 int leaf_gemm_bf16(leaf_handle_t h, const void* A, const void* Bt, const float* bias, void* C,
                    int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t act, const int32_t* m_dev,
                    void* stream);
+/* y[rows,W] (bf16) = LayerNorm(x[rows,W] fp32) with the tower's kernel; W = cfg.width. */
+int leaf_test_layernorm(leaf_handle_t h, const float* x, int32_t rows, const float* gamma, const float* beta, void* y,
+                        void* stream);
+/* out[rows,W] (bf16) = causal attention over packed qkv[rows,3W] (bf16) with sequence offsets cu[N+1]. */
+int leaf_test_attention(leaf_handle_t h, const void* qkv, const int32_t* cu, int32_t N, void* out, void* stream);
 /* Number of kernels the engine has launched since the last call with reset != 0. */
 int64_t leaf_launch_count(leaf_handle_t h, int32_t reset);
-/* Packed-row count of the last leaf_encode (device int32[1], asynchronous w.r.t. the host). */
-const int32_t* leaf_last_rows_dev(leaf_handle_t h);
+/* Packed-row count (sum of len) of the last leaf_encode; synchronises the device. */
+int64_t leaf_last_rows(leaf_handle_t h);
 /* Accumulated device time (ms) of kernels in class `which` (0 = GEMM) between CUDA events, when
  * timing was enabled with leaf_set_timing(h, 1). Synchronises the stream. */
 int leaf_set_timing(leaf_handle_t h, int32_t on);

@@ -46,6 +46,7 @@ struct GemmParams {
   void* C;                // bf16 or fp32 [M, ldc]
   int ldc;
   int act;
+  uint32_t tx_bytes;      // bytes one pipeline stage receives (TMA boxes are clamped to small tensors)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -204,7 +205,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
           mbar_wait(empty_bar(stage), phase ^ 1);
           const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
           const uint32_t sb = sa + GEMM_A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), GEMM_STAGE_BYTES);
+          mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
           tma_load_2d(sa, &tmap_a, full_bar(stage), kb * GEMM_BK, m_blk * GEMM_BM);
           tma_load_2d(sb, &tmap_b, full_bar(stage), kb * GEMM_BK, n_blk * GEMM_BN);
           if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }

@@ -1,0 +1,89 @@
+// K1 kernel: candidate expansion + CLIP BPE tokenization, one warp per candidate (sm_100a).
+//   lanes 0..31 copy the caption into shared memory with 16-byte loads when the source is aligned,
+//   lane 0 applies the edit, unescapes, cleans and splits (serial, a few hundred byte operations),
+//   lanes take regex pieces round-robin and run the BPE merge loop on them (merge ranks from an L2-resident
+//   1 MiB hash table: the 48 894-entry table does not fit a CTA's shared memory next to the scratch),
+//   lane 0 assembles the 77-slot row; all lanes store it (coalesced int32).
+// The scalar pieces are k1_core.cuh, which the CPU test-suite pins against the reference's tokenizer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "k1_core.cuh"
+
+namespace leaf {
+
+constexpr int K1_WARPS_PER_CTA = 4;
+
+struct K1Args {
+  const uint8_t* caps;
+  const int32_t* cap_off;
+  int B, n;
+  const int32_t* pos;
+  const int32_t* chr;
+  const int32_t* sel;
+  const uint8_t* valid;
+  int32_t* tok_out;
+  int32_t* len_out;
+  int32_t* status_out;
+};
+
+__global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32) k1_expand_tokenize_kernel(const K1Tables T, const K1Args a) {
+  __shared__ __align__(16) uint8_t s_src[K1_WARPS_PER_CTA][K1_MAX_TEXT];
+  __shared__ __align__(16) uint8_t s_a[K1_WARPS_PER_CTA][K1_MAX_TEXT];
+  __shared__ __align__(16) uint8_t s_b[K1_WARPS_PER_CTA][K1_MAX_TEXT];
+  __shared__ uint16_t s_sym[K1_WARPS_PER_CTA][2 * K1_MAX_TEXT];
+  __shared__ uint16_t s_rk[K1_WARPS_PER_CTA][2 * K1_MAX_TEXT];
+  __shared__ uint16_t s_ps[K1_WARPS_PER_CTA][K1_MAX_PIECES];
+  __shared__ uint16_t s_pl[K1_WARPS_PER_CTA][K1_MAX_PIECES];
+  __shared__ int32_t s_row[K1_WARPS_PER_CTA][K1_CTX + 3];
+  __shared__ int s_meta[K1_WARPS_PER_CTA][4];
+
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = a.n > 0 ? a.n : 1;
+  const int R = a.B * per;
+  const int r = blockIdx.x * K1_WARPS_PER_CTA + w;
+  if (r >= R) return;
+  const int b = r / per;
+  const int off = a.cap_off[b];
+  int len = a.cap_off[b + 1] - off;
+  int flags = 0;
+  if (len > 1000) { flags |= K1_FLAG_TOO_LONG; len = 0; }
+  const uint8_t* src = a.caps + off;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    for (int i = lane * 16; i < len; i += 32 * 16)        // may read up to 15 bytes past the caption: callers pad
+      *reinterpret_cast<uint4*>(&s_src[w][i]) = __ldg(reinterpret_cast<const uint4*>(src + i));
+  } else {
+    for (int i = lane; i < len; i += 32) s_src[w][i] = __ldg(src + i);
+  }
+  __syncwarp();
+
+  K1Scratch S{s_a[w], s_b[w], s_sym[w], s_rk[w], s_ps[w], s_pl[w], 0, 0};
+  if (lane == 0) {
+    bool edit = a.n > 0 && (!a.valid || a.valid[r]);
+    int z = 0, c = -1;
+    if (a.n > 0) {
+      z = a.sel ? a.pos[b * a.n + a.sel[b]] : a.pos[r];
+      c = a.chr[r];
+      if (z < 0 || z > 2 * len) { edit = false; flags |= K1_FLAG_TOO_LONG; }
+    }
+    flags |= k1_prepare(T, s_src[w], len, edit, z, c, S);
+    s_meta[w][0] = S.text_len;
+    s_meta[w][1] = S.n_pieces;
+  }
+  __syncwarp();
+  S.text_len = s_meta[w][0];
+  S.n_pieces = s_meta[w][1];
+  for (int p = lane; p < S.n_pieces; p += 32) k1_encode_piece(T, S, p);
+  __syncwarp();
+  if (lane == 0) {
+    s_meta[w][2] = k1_emit_row(S, s_row[w]);
+    if (flags && a.status_out) atomicOr(a.status_out, flags);
+  }
+  __syncwarp();
+  int32_t* out = a.tok_out + static_cast<size_t>(r) * K1_CTX;
+  for (int i = lane; i < K1_CTX; i += 32) out[i] = s_row[w][i];
+  if (lane == 0) a.len_out[r] = s_meta[w][2];
+}
+
+}  // namespace leaf

@@ -1,0 +1,272 @@
+"""Host-side wrapper of the native engine: owns a leaf_handle_t, binds a text tower's live parameters and exposes
+the three duck-typed pieces of the reference's seam:
+
+    tokenizer(list[str]) -> LongTensor[N,77]          /root/reference/src/open_clip/tokenizer.py:226-265
+    model.encode_text(tokens, normalize) -> [N,E]     /root/reference/src/open_clip/model.py:269-284
+    attack_text_leaf(...)                              /root/reference/utils_attacks.py:297-393  (leaf_b200/attack.py)
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed only; all compute is in
+leaf_b200/lib/libleaf_b200.so, and nothing here runs without it and a B200.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import LeafCfg, LeafLayerPtrs, LeafWeightPtrs, LeafError, check
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MERGES_BIN = os.path.join(HERE, "data", "clip_bpe_merges.bin")
+
+CONTEXT_LENGTH = 77
+OBJECTIVES = {"l2": 0, "negl2": 1, "sim": 2, "dissim": 3}
+STATUS_ENTITY_DOMAIN, STATUS_NON_ASCII, STATUS_TOO_LONG = 1, 2, 4
+MAX_CAPTION_BYTES = 1000
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _canon_state(params: dict):
+    """Map a parameter dict in open_clip CLIP / CustomTextCLIP ('text.' prefix) / HF CLIPTextModel(WithProjection)
+    naming to canonical per-tensor entries (conversion/convert_2.py:37-99)."""
+    keys = params.keys()
+    if any(k.endswith("embeddings.token_embedding.weight") for k in keys):       # HF layout
+        pre = next(k for k in keys if k.endswith("embeddings.token_embedding.weight"))
+        pre = pre[: -len("embeddings.token_embedding.weight")]                    # "text_model." or "...text_model."
+        root = pre[: -len("text_model.")] if pre.endswith("text_model.") else pre
+        out = {"layout": "hf", "tok": params[pre + "embeddings.token_embedding.weight"],
+               "pos": params[pre + "embeddings.position_embedding.weight"],
+               "lnf_w": params[pre + "final_layer_norm.weight"], "lnf_b": params[pre + "final_layer_norm.bias"],
+               "proj": params[root + "text_projection.weight"], "proj_is_ew": 1, "layers": []}
+        i = 0
+        while (pre + f"encoder.layers.{i}.layer_norm1.weight") in params:
+            p = pre + f"encoder.layers.{i}."
+            g = lambda s: params[p + s]
+            out["layers"].append(dict(
+                ln1_w=g("layer_norm1.weight"), ln1_b=g("layer_norm1.bias"),
+                q_w=g("self_attn.q_proj.weight"), k_w=g("self_attn.k_proj.weight"), v_w=g("self_attn.v_proj.weight"),
+                q_b=g("self_attn.q_proj.bias"), k_b=g("self_attn.k_proj.bias"), v_b=g("self_attn.v_proj.bias"),
+                out_w=g("self_attn.out_proj.weight"), out_b=g("self_attn.out_proj.bias"),
+                ln2_w=g("layer_norm2.weight"), ln2_b=g("layer_norm2.bias"),
+                fc1_w=g("mlp.fc1.weight"), fc1_b=g("mlp.fc1.bias"), fc2_w=g("mlp.fc2.weight"), fc2_b=g("mlp.fc2.bias")))
+            i += 1
+        return out
+    pre = "text." if "text.token_embedding.weight" in params else ""
+    if (pre + "token_embedding.weight") not in params:
+        raise LeafError("unrecognised parameter naming: expected open_clip (token_embedding.weight / "
+                        "text.token_embedding.weight) or HF CLIPTextModel keys")
+    out = {"layout": "open_clip", "tok": params[pre + "token_embedding.weight"], "pos": params[pre + "positional_embedding"],
+           "lnf_w": params[pre + "ln_final.weight"], "lnf_b": params[pre + "ln_final.bias"],
+           "proj": params[pre + "text_projection"], "proj_is_ew": 0, "layers": []}
+    if out["proj"].dim() == 2 and (pre + "text_projection.weight") in params:     # nn.Linear projection variant
+        out["proj"], out["proj_is_ew"] = params[pre + "text_projection.weight"], 1
+    i = 0
+    while (pre + f"transformer.resblocks.{i}.ln_1.weight") in params:
+        p = pre + f"transformer.resblocks.{i}."
+        g = lambda s: params[p + s]
+        out["layers"].append(dict(
+            ln1_w=g("ln_1.weight"), ln1_b=g("ln_1.bias"), in_proj_w=g("attn.in_proj_weight"), in_proj_b=g("attn.in_proj_bias"),
+            out_w=g("attn.out_proj.weight"), out_b=g("attn.out_proj.bias"), ln2_w=g("ln_2.weight"), ln2_b=g("ln_2.bias"),
+            fc1_w=g("mlp.c_fc.weight"), fc1_b=g("mlp.c_fc.bias"), fc2_w=g("mlp.c_proj.weight"), fc2_b=g("mlp.c_proj.bias")))
+        i += 1
+    return out
+
+
+class LeafEngine:
+    """One engine = one text tower on one GPU. `params` is a dict name -> CUDA fp32 tensor (e.g.
+    dict(model.named_parameters()) or a state_dict) in open_clip or HF naming; the tensors stay owned by the
+    caller and are read in place (call refresh_weights() after every optimizer step)."""
+
+    def __init__(self, params: dict, heads: int, quick_gelu: bool = False, ln_eps: float = 1e-5, max_seqs: int = 0):
+        if not torch.cuda.is_available():
+            raise LeafError("leaf_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self._lib = _native.lib()
+        c = _canon_state(params)
+        self._canon = c
+        self.width = int(c["tok"].shape[1])
+        self.layers = len(c["layers"])
+        self.heads = int(heads)
+        self.embed_dim = int(c["proj"].shape[0] if c["proj_is_ew"] else c["proj"].shape[1])
+        self.device = c["tok"].device
+        self._check_tensors()
+        cfg = LeafCfg(self.width, self.layers, self.heads, self.embed_dim, 1 if quick_gelu else 0, ln_eps)
+        self._h = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+            pairs = np.fromfile(MERGES_BIN, dtype="<u4")
+            check(self._lib.leaf_load_bpe(self._h, pairs.ctypes.data_as(ctypes.c_void_p), len(pairs)))
+            self._bind()
+        self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.max_seqs = 0
+        if max_seqs:
+            self.reserve(max_seqs)
+
+    # ---- lifetime ----------------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._lib.leaf_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check_tensors(self):
+        c = self._canon
+        flat = [c["tok"], c["pos"], c["lnf_w"], c["lnf_b"], c["proj"]] + [t for l in c["layers"] for t in l.values()]
+        for t in flat:
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise LeafError("tower parameters must be contiguous fp32 CUDA tensors")
+            if t.data_ptr() % 16:
+                raise LeafError("tower parameters must be 16-byte aligned")
+        if self.width != self.heads * 64:
+            raise LeafError(f"head_dim must be 64 (width {self.width}, heads {self.heads})")
+
+    def _bind(self):
+        c = self._canon
+        arr = (LeafLayerPtrs * self.layers)()
+        for i, l in enumerate(c["layers"]):
+            for k, _ in LeafLayerPtrs._fields_:
+                setattr(arr[i], k, l[k].data_ptr() if k in l else None)
+        wp = LeafWeightPtrs(c["tok"].data_ptr(), c["pos"].data_ptr(), c["lnf_w"].data_ptr(), c["lnf_b"].data_ptr(),
+                            c["proj"].data_ptr(), c["proj_is_ew"], arr)
+        self._keep = (arr, wp)
+        check(self._lib.leaf_bind_weights(self._h, ctypes.byref(wp), _stream()))
+
+    def refresh_weights(self):
+        """Re-cast the bf16 operand copies from the live fp32 parameters (after optimizer.step())."""
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_refresh_weights(self._h, _stream()))
+
+    def reserve(self, max_seqs: int):
+        if max_seqs > self.max_seqs:
+            with torch.cuda.device(self.device):
+                check(self._lib.leaf_reserve(self._h, int(max_seqs)))
+            self.max_seqs = int(max_seqs)
+
+    # ---- K1 ----------------------------------------------------------------------------------------------
+    @staticmethod
+    def pack_captions(sentences):
+        """list[str] -> (uint8 caption bytes back to back, int32 [B+1] offsets). The buffer tail is padded so the
+        kernel's 16-byte loads never leave the allocation."""
+        blobs = []
+        for s in sentences:
+            try:
+                b = s.encode("ascii")
+            except UnicodeEncodeError as ex:
+                raise LeafError(f"caption outside the tokenizer kernel's ASCII domain: {s!r}") from ex
+            if len(b) > MAX_CAPTION_BYTES:
+                raise LeafError(f"caption longer than {MAX_CAPTION_BYTES} bytes")
+            blobs.append(b)
+        off = np.zeros(len(blobs) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(b) for b in blobs])
+        data = np.frombuffer(b"".join(blobs) + b"\0" * 32, dtype=np.uint8)
+        return data, off
+
+    def upload_captions(self, sentences):
+        data, off = self.pack_captions(sentences)
+        d = torch.from_numpy(data.copy()).pin_memory().to(self.device, non_blocking=True)
+        o = torch.from_numpy(off).pin_memory().to(self.device, non_blocking=True)
+        return d, o
+
+    def expand_tokenize(self, caps_dev, off_dev, B, n, pos=None, chr_=None, sel=None, valid=None):
+        """leaf_expand_tokenize on device tensors; returns (tokens int32 [R,77], lengths int32 [R])."""
+        R = B * max(n, 1)
+        tok = torch.empty((R, CONTEXT_LENGTH), dtype=torch.int32, device=self.device)
+        ln = torch.empty((R,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_expand_tokenize(self._h, _ptr(caps_dev), _ptr(off_dev), B, n, _ptr(pos), _ptr(chr_), _ptr(sel),
+                                                 _ptr(valid), _ptr(tok), _ptr(ln), _ptr(self._status), _stream()))
+        return tok, ln
+
+    def check_status(self):
+        """Synchronising read of the tokenizer status flags; raises on inputs outside the kernel's closed domain."""
+        st = int(self._status.item())
+        if st:
+            self._status.zero_()
+            what = [m for bit, m in ((1, "an html entity expanded outside U+0000..U+00FF"),
+                                     (2, "non-ASCII caption byte"), (4, "caption too long / position out of range")) if st & bit]
+            raise LeafError("tokenizer kernel: " + "; ".join(what))
+
+    def tokenize(self, texts, check=True) -> torch.Tensor:
+        """SimpleTokenizer.__call__ (tokenizer.py:226-265): int64 [N,77] on the engine's device."""
+        if isinstance(texts, str):
+            texts = [texts]
+        d, o = self.upload_captions(texts)
+        tok, _ = self.expand_tokenize(d, o, len(texts), 0)
+        if check:
+            self.check_status()
+        return tok.long()
+
+    # ---- K2 ----------------------------------------------------------------------------------------------
+    def encode_tokens(self, tok: torch.Tensor, lengths: torch.Tensor = None, normalize: bool = False) -> torch.Tensor:
+        """CLIP.encode_text (model.py:269-284) for token rows already on the device."""
+        if tok.dtype != torch.int32:
+            tok = tok.to(torch.int32)
+        tok = tok.contiguous()
+        N = tok.shape[0]
+        if lengths is None:
+            lengths = (tok.argmax(dim=-1) + 1).to(torch.int32)      # transformer.py:661
+        self.reserve(N)
+        out = torch.empty((N, self.embed_dim), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_encode(self._h, _ptr(tok), _ptr(lengths.contiguous()), N, 1 if normalize else 0, _ptr(out), _stream()))
+        return out
+
+    # ---- K3 ----------------------------------------------------------------------------------------------
+    def score(self, feats: torch.Tensor, anchor: torch.Tensor, B: int, n: int, objective: str = "l2", want_loss=False):
+        """utils_attacks.py:332-348: returns (best int32 [B], best_feat [B,E], loss [B,n] or None)."""
+        best = torch.empty((B,), dtype=torch.int32, device=self.device)
+        best_feat = torch.empty((B, self.embed_dim), dtype=torch.float32, device=self.device)
+        loss = torch.empty((B, n), dtype=torch.float32, device=self.device) if want_loss else None
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_score(self._h, _ptr(feats), _ptr(anchor), B, n, OBJECTIVES[objective], _ptr(loss), _ptr(best),
+                                       _ptr(best_feat), _stream()))
+        return best, best_feat, loss
+
+    # ---- hooks for tests / bench ---------------------------------------------------------------------------
+    def gemm(self, A, Bt, bias=None, epilogue=0, act=0, C=None, m_dev=None):
+        M, K = A.shape
+        N = Bt.shape[0]
+        if C is None:
+            C = torch.empty((M, N), dtype=torch.bfloat16 if epilogue in (0, 1) else torch.float32, device=A.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_gemm_bf16(self._h, _ptr(A), _ptr(Bt), _ptr(bias), _ptr(C), M, N, K, epilogue, act, _ptr(m_dev), _stream()))
+        return C
+
+    def test_layernorm(self, x, gamma, beta):
+        y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+        check(self._lib.leaf_test_layernorm(self._h, _ptr(x), x.shape[0], _ptr(gamma), _ptr(beta), _ptr(y), _stream()))
+        return y
+
+    def test_attention(self, qkv, cu):
+        out = torch.empty((qkv.shape[0], self.width), dtype=torch.bfloat16, device=qkv.device)
+        check(self._lib.leaf_test_attention(self._h, _ptr(qkv), _ptr(cu), cu.shape[0] - 1, _ptr(out), _stream()))
+        return out
+
+    def launch_count(self, reset=False) -> int:
+        return int(self._lib.leaf_launch_count(self._h, 1 if reset else 0))
+
+    def set_timing(self, on: bool):
+        check(self._lib.leaf_set_timing(self._h, 1 if on else 0))
+
+    def gemm_time_ms(self):
+        n = ctypes.c_int32(0)
+        ms = self._lib.leaf_timing_ms(self._h, 0, ctypes.byref(n))
+        return float(ms), int(n.value)
+
+    def last_rows(self) -> int:
+        """Packed token rows (sum of argmax(ids)+1) of the last encode; synchronises."""
+        return int(self._lib.leaf_last_rows(self._h))

@@ -1,0 +1,197 @@
+"""GPU parity tests of the individual kernels, through the C ABI (leaf_b200/lib/libleaf_b200.so).
+Floating-point kernels are compared with a plain fp32 torch restatement of the same op on the same bf16-rounded
+inputs (tolerances stated per test); the integer tokenizer kernel must equal the oracle bit for bit."""
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from leaf_b200 import synth
+    from leaf_b200.tower import LeafTextTower
+    tower = LeafTextTower.random("small", seed=3)
+    return tower.leaf_engine
+
+
+def _gelu_ref(x, act):
+    return x * torch.sigmoid(1.702 * x) if act == 1 else torch.nn.functional.gelu(x)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (300, 384, 128), (77, 64, 128), (1000, 3072, 1024),
+                                   (4096, 1024, 4096), (20000, 768, 768), (129, 1280, 5120)])
+def test_gemm_epilogues(eng, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + K)
+    A = (torch.randn((M, K), generator=g, device="cuda") * 0.5).to(torch.bfloat16)
+    Bt = (torch.randn((N, K), generator=g, device="cuda") * (K ** -0.5)).to(torch.bfloat16)
+    bias = torch.randn((N,), generator=g, device="cuda") * 0.1
+    ref = A.float() @ Bt.float().T
+    # bf16 store
+    C = eng.gemm(A, Bt, None, epilogue=0)
+    torch.cuda.synchronize()
+    # tolerance: bf16 output rounding (2^-8 relative) on values of magnitude <= ~4
+    assert torch.allclose(C.float(), ref, atol=2e-2, rtol=1e-2), (C.float() - ref).abs().max().item()
+    # fp32 store + bias: fp32 accumulation order differs from torch only
+    C32 = eng.gemm(A, Bt, bias, epilogue=3)
+    assert torch.allclose(C32, ref + bias, atol=2e-3, rtol=1e-3), (C32 - ref - bias).abs().max().item()
+    # activation epilogues
+    for act in (0, 1):
+        Ca = eng.gemm(A, Bt, bias, epilogue=1, act=act)
+        want = _gelu_ref(ref + bias, act)
+        assert torch.allclose(Ca.float(), want, atol=2e-2, rtol=1e-2), (act, (Ca.float() - want).abs().max().item())
+    # residual: C += A.Bt^T + bias, rows beyond a device-side row count untouched
+    m_live = max(1, M - 37)
+    m_dev = torch.tensor([m_live], dtype=torch.int32, device="cuda")
+    R = torch.randn((M, N), generator=g, device="cuda")
+    R0 = R.clone()
+    eng.gemm(A, Bt, bias, epilogue=2, C=R, m_dev=m_dev)
+    torch.cuda.synchronize()
+    assert torch.allclose(R[:m_live], R0[:m_live] + ref[:m_live] + bias, atol=2e-3, rtol=1e-3)
+    assert torch.equal(R[m_live:], R0[m_live:])
+
+
+def test_gemm_duplicate_rows_bitwise_equal(eng):
+    """Numerics must not depend on a row's position (hard part 5): duplicate candidates must tie."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    row = torch.randn((1, 1024), generator=g, device="cuda").to(torch.bfloat16)
+    A = row.repeat(777, 1).contiguous()
+    Bt = (torch.randn((1024, 1024), generator=g, device="cuda") / 32).to(torch.bfloat16)
+    C = eng.gemm(A, Bt, None, epilogue=3)
+    assert torch.equal(C, C[0:1].expand_as(C))
+
+
+def test_layernorm(eng):
+    g = torch.Generator(device="cuda").manual_seed(1)
+    W = eng.width
+    x = torch.randn((1000, W), generator=g, device="cuda") * 3 + 0.5
+    gamma = 1 + 0.1 * torch.randn((W,), generator=g, device="cuda")
+    beta = 0.1 * torch.randn((W,), generator=g, device="cuda")
+    y = eng.test_layernorm(x, gamma, beta)
+    ref = torch.nn.functional.layer_norm(x, (W,), gamma, beta, 1e-5)
+    # bf16 rounding of the output only
+    assert torch.allclose(y.float(), ref, atol=3e-2, rtol=8e-3)
+
+
+def test_attention_varlen_causal(eng):
+    g = torch.Generator(device="cuda").manual_seed(2)
+    W, H = eng.width, eng.heads
+    lens = [1, 2, 13, 77, 40, 5, 77, 3]
+    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    rows = int(cu[-1])
+    qkv = torch.randn((rows, 3 * W), generator=g, device="cuda").to(torch.bfloat16)
+    out = eng.test_attention(qkv, cu).float()
+    for i, t in enumerate(lens):
+        s = int(cu[i])
+        q, k, v = qkv[s:s + t].float().split(W, dim=-1)
+        q, k, v = (z.view(t, H, 64).transpose(0, 1) for z in (q, k, v))
+        att = (q @ k.transpose(-1, -2)) * 0.125 + torch.full((t, t), float("-inf"), device="cuda").triu_(1)
+        ref = (torch.softmax(att, -1) @ v).transpose(0, 1).reshape(t, W)
+        assert torch.allclose(out[s:s + t], ref, atol=2e-2, rtol=1e-2), i
+
+
+def test_score_argmax(eng):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    E = eng.embed_dim
+    B, n = 9, 50
+    feats = torch.randn((B * n, E), generator=g, device="cuda")
+    feats[7] = feats[3]                       # exact tie inside sample 0 -> first index must win
+    anchor = torch.randn((B, E), generator=g, device="cuda")
+    for obj in ("l2", "negl2", "sim", "dissim"):
+        best, bf, loss = eng.score(feats, anchor, B, n, obj, want_loss=True)
+        f = feats.view(B, n, E)
+        if obj in ("l2", "negl2"):
+            ref = ((f - anchor.view(B, 1, E)) ** 2).sum(-1)
+        else:
+            ref = (f @ anchor.view(B, E, 1)).squeeze(-1)
+        if obj in ("negl2", "dissim"):
+            ref = -ref
+        assert torch.allclose(loss, ref, rtol=1e-4, atol=1e-4)
+        assert torch.equal(best.long(), torch.argmax(loss, dim=-1))
+        assert torch.equal(bf, f[torch.arange(B), best.long()])
+    f = feats.clone()
+    f[3] = f[7] = anchor[0] + 100.0
+    best, _, _ = eng.score(f, anchor, B, n, "l2")
+    assert int(best[0]) == 3
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# K1: bit-exact against the oracle / reference goldens
+# ----------------------------------------------------------------------------------------------------------------
+def _k1(eng, caps, n=0, pos=None, chr_=None, sel=None, valid=None):
+    d, o = eng.upload_captions(caps)
+    t = lambda a, dt: None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
+    tok, ln = eng.expand_tokenize(d, o, len(caps), n, t(pos, torch.int32), t(chr_, torch.int32), t(sel, torch.int32),
+                                  t(valid, torch.uint8))
+    torch.cuda.synchronize()
+    return tok.cpu().numpy(), ln.cpu().numpy()
+
+
+def test_k1_golden_strings(eng, golden_dir):
+    from oracle import leaf_oracle as O
+    import html
+    g = json.load(open(os.path.join(golden_dir, "tokenizer_golden.json")))
+    texts = [t for t, _ in g["encode"] if len(t) <= 1000 and all(ord(c) < 128 for c in t)
+             and all(ord(c) <= 0xFF for c in html.unescape(t) + html.unescape(html.unescape(t)))]
+    assert len(texts) > 2000
+    want = O.OracleTokenizer()(texts).numpy()
+    tok, ln = _k1(eng, texts)
+    eng._status.zero_()
+    assert (tok == want).all()
+    assert (ln == want.argmax(1) + 1).all()
+    tok, ln = _k1(eng, g["rows_in"])
+    assert tok.tolist() == g["rows"]
+
+
+def test_k1_candidates_bit_exact(eng):
+    from leaf_b200 import synth
+    from oracle import leaf_oracle as O
+    rng = random.Random(5)
+    otok = O.OracleTokenizer()
+    V = synth.V_DEFAULT
+    for kind, B, n in (("typical", 32, 50), ("dense-77", 6, 50), ("short", 12, 120)):
+        caps = synth.make_captions(B, seed=9, kind=kind)
+        pos = np.array([[rng.randint(0, 2 * len(S)) for _ in range(n)] for S in caps], dtype=np.int32)
+        chr_ = np.array([[V[rng.randrange(len(V))] for _ in range(n)] for _ in caps], dtype=np.int32)
+        valid = np.ones((B, n), dtype=np.uint8)
+        valid[:, 5::7] = 0
+        tok, ln = _k1(eng, caps, n, pos, chr_, valid=valid)
+        strings = [O.edit_sentence(S, int(pos[b, j]), int(chr_[b, j])) if valid[b, j] else S
+                   for b, S in enumerate(caps) for j in range(n)]
+        want = otok(strings).numpy()
+        assert (tok == want).all(), kind
+        assert (ln == want.argmax(1) + 1).all()
+        sel = np.array([rng.randrange(n) for _ in caps], dtype=np.int32)
+        tok, ln = _k1(eng, caps, n, pos, chr_, sel=sel)
+        strings = [O.edit_sentence(S, int(pos[b, sel[b]]), int(chr_[b, j])) for b, S in enumerate(caps) for j in range(n)]
+        assert (tok == otok(strings).numpy()).all(), kind
+    eng._status.zero_()
+
+
+def test_k1_flags_out_of_domain(eng):
+    from leaf_b200 import LeafError
+    with pytest.raises(LeafError):
+        eng.tokenize(["café"])
+    with pytest.raises(LeafError):
+        eng.tokenize(["x &lambda; y"])
+    assert eng.tokenize(["x &lt; y"]).shape == (1, 77)
+
+
+def test_k1_matches_cpu_compiled_core_at_full_size(eng):
+    """BASELINE config size (B=128, n=50): the device kernel against the same scalar core compiled for the CPU."""
+    from leaf_b200 import synth
+    from tests import k1_harness as H
+    rng = np.random.RandomState(0)
+    caps = synth.make_captions(128, seed=0, kind="typical")
+    n = 50
+    pos = np.stack([rng.randint(0, 2 * len(S) + 1, size=n) for S in caps]).astype(np.int32)
+    chr_ = np.array(synth.V_DEFAULT, dtype=np.int32)[rng.randint(0, 96, size=(128, n))]
+    tok, ln = _k1(eng, caps, n, pos, chr_)
+    htok, hln, _ = H.expand_tokenize(caps, n, pos, chr_)
+    assert (tok == htok).all() and (ln == hln).all()
+    eng._status.zero_()
