@@ -104,19 +104,26 @@ int leaf_reserve(leaf_handle_t h, int32_t max_seqs);
  *   chr  [B,n]   : code point to write, -1 = delete (V[u], train_AT_text_only.py:93)
  *   valid[B,n]   : 0 => candidate is replaced by the unedited caption (:325); NULL = all valid
  *   n == 0       : tokenize the B captions themselves (tokenizer(texts), utils_AT.py:296,312)
- *   tok_out [R,77] int32 zero padded, R = B*max(n,1); len_out[R] = argmax(ids)+1 (transformer.py:661)
+ *   tok_out [R,77] int32 zero padded; len_out[R] = argmax(ids)+1 (transformer.py:661).
+ *                  n == 0: R = B. n > 0: R = B*n + B - the B*n candidates (sample-major) followed by the B unedited
+ *                  captions, whose hidden states the candidates share up to the edited word (see leaf_encode);
+ *   base_out [R] : (may be NULL) for candidate rows the index of their sample's caption row (B*n + b), else -1
  * Token ids equal SimpleTokenizer's bit for bit. status_out (device int32[1], may be NULL) gets
  * OR-ed flags: 1 = an html entity expanded outside U+0000..U+00FF, 2 = non-ASCII caption byte. */
 int leaf_expand_tokenize(leaf_handle_t h, const uint8_t* caps, const int32_t* cap_off, int32_t B, int32_t n,
                          const int32_t* pos, const int32_t* chr, const int32_t* sel, const uint8_t* valid,
-                         int32_t* tok_out, int32_t* len_out, int32_t* status_out, void* stream);
+                         int32_t* tok_out, int32_t* len_out, int32_t* base_out, int32_t* status_out, void* stream);
 
 /* ---- K2: text tower forward -------------------------------------------------------------------
  * Replaces CLIP.encode_text(tokens, normalize) (model.py:269-284; transformer.py:254-265,355-366,
  * 653-665). tok [N,77] int32, len [N] (positions after argmax(ids) are dead under the causal mask and
- * are not computed). feat_out [N,E] fp32. bf16 tensor-core GEMMs, fp32 accumulate/residual/LN/softmax. */
-int leaf_encode(leaf_handle_t h, const int32_t* tok, const int32_t* len, int32_t N, int32_t normalize,
-                float* feat_out, void* stream);
+ * are not computed). feat_out [N,E] fp32. bf16 tensor-core GEMMs, fp32 accumulate/residual/LN/softmax.
+ * base [N] (may be NULL): base[i] = j >= 0 names another row of this batch (with base[j] = -1) that row i was
+ * derived from; positions where both token rows agree have identical hidden states under the causal mask, so
+ * they are computed once (on row j) and row i's attention reads row j's keys/values for them. Results are
+ * bit-identical to base == NULL. */
+int leaf_encode(leaf_handle_t h, const int32_t* tok, const int32_t* len, const int32_t* base, int32_t N,
+                int32_t normalize, float* feat_out, void* stream);
 
 /* ---- K3: TextFARE score + per-sample argmax ----------------------------------------------------
  * Replaces utils_attacks.py:332-348 / :370-386 / :393. feat [B*n,E] fp32, anchor [B,E] fp32.
@@ -135,8 +142,9 @@ int leaf_gemm_bf16(leaf_handle_t h, const void* A, const void* Bt, const float* 
 /* y[rows,W] (bf16) = LayerNorm(x[rows,W] fp32) with the tower's kernel; W = cfg.width. */
 int leaf_test_layernorm(leaf_handle_t h, const float* x, int32_t rows, const float* gamma, const float* beta, void* y,
                         void* stream);
-/* out[rows,W] (bf16) = causal attention over packed qkv[rows,3W] (bf16) with sequence offsets cu[N+1]. */
-int leaf_test_attention(leaf_handle_t h, const void* qkv, const int32_t* cu, int32_t N, void* out, void* stream);
+/* out[rows,W] (bf16) = causal attention over packed qkv[rows,3W] (bf16); meta [N,4] int32 = {own_row, t, p, base_row}
+ * per sequence (positions [p,t) are rows own_row.., keys/values of [0,p) are rows base_row..). */
+int leaf_test_attention(leaf_handle_t h, const void* qkv, const int32_t* meta, int32_t N, void* out, void* stream);
 /* Number of kernels the engine has launched since the last call with reset != 0. */
 int64_t leaf_launch_count(leaf_handle_t h, int32_t reset);
 /* Packed-row count (sum of len) of the last leaf_encode; synchronises the device. */

@@ -105,7 +105,7 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
         anchor /= anchor.norm(dim=-1, keepdim=True)                           # in place, as :304-308
     anchor = anchor.to(device=dev, dtype=torch.float32).contiguous()
     normalize = objective in ("sim", "dissim")
-    eng.reserve(B * n)
+    eng.reserve(B * n + B)
     best_feat = None
     for _ in range(k):
         lens = [len(S) for S in sentences]
@@ -122,8 +122,8 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
         if valid_fn is not None:
             SS = [[generate_sentence(S, int(z), 32) for z in positions[i]] for i, S in enumerate(sentences)]
             valid1 = _valid_mask(valid_fn, sentences, SS, B, n, dev)
-        tok, ln = eng.expand_tokenize(caps_d, off_d, B, n, pos=pos_d, chr_=chr1_d, valid=valid1)
-        feats = eng.encode_tokens(tok, ln, normalize)
+        tok, ln, base = eng.expand_tokenize(caps_d, off_d, B, n, pos=pos_d, chr_=chr1_d, valid=valid1)
+        feats = eng.encode_tokens(tok, ln, normalize, base)          # rows [0, B*n) candidates, then the B captions
         best1, _, loss1 = eng.score(feats, anchor, B, n, objective, want_loss=debug)
         # --- phase 2: choose the character at the best position, :355-389 ---
         valid2 = None
@@ -132,8 +132,8 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
             zs = positions[np.arange(B), b1]
             SS = [[generate_sentence(S, int(zs[i]), int(c)) for c in chars2[i]] for i, S in enumerate(sentences)]
             valid2 = _valid_mask(valid_fn, sentences, SS, B, n, dev)
-        tok, ln = eng.expand_tokenize(caps_d, off_d, B, n, pos=pos_d, chr_=chr2_d, sel=best1, valid=valid2)
-        feats = eng.encode_tokens(tok, ln, normalize)
+        tok, ln, base = eng.expand_tokenize(caps_d, off_d, B, n, pos=pos_d, chr_=chr2_d, sel=best1, valid=valid2)
+        feats = eng.encode_tokens(tok, ln, normalize, base)
         best2, best_feat, loss2 = eng.score(feats, anchor, B, n, objective, want_loss=debug)
         # --- one small D2H per round: the 2B winner indices (+ tokenizer status) ---
         picks = torch.stack([best1, best2]).cpu().numpy()

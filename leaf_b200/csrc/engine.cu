@@ -72,7 +72,8 @@ struct leaf_engine {
   __nv_bfloat16* h = nullptr;         // [rows_cap, W]  LN output / attention output
   __nv_bfloat16* big = nullptr;       // [rows_cap, 4W] qkv (3W) or MLP hidden (4W)
   __nv_bfloat16* pooled = nullptr;    // [max_seqs, W]
-  int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr;
+  int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr;
+  int4* meta = nullptr;
   // bookkeeping
   int64_t launches = 0;
   bool timing = false;
@@ -180,9 +181,10 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
 
 static void free_workspace(leaf_engine* e) {
   cudaFree(e->x); cudaFree(e->h); cudaFree(e->big); cudaFree(e->pooled);
-  cudaFree(e->cu); cudaFree(e->eos_row); cudaFree(e->total_rows);
+  cudaFree(e->cu); cudaFree(e->eos_row); cudaFree(e->total_rows); cudaFree(e->pfx); cudaFree(e->own_len); cudaFree(e->meta);
   e->x = nullptr; e->h = nullptr; e->big = nullptr; e->pooled = nullptr;
-  e->cu = e->eos_row = e->total_rows = nullptr;
+  e->cu = e->eos_row = e->total_rows = e->pfx = e->own_len = nullptr;
+  e->meta = nullptr;
   e->max_seqs = 0; e->rows_cap = 0;
   e->tmaps.clear();
 }
@@ -333,6 +335,9 @@ extern "C" int leaf_reserve(leaf_handle_t e, int32_t max_seqs) {
   CK(cudaMalloc(&e->pooled, (static_cast<size_t>(max_seqs) + 128) * W * 2));
   CK(cudaMalloc(&e->cu, (static_cast<size_t>(max_seqs) + 1) * 4));
   CK(cudaMalloc(&e->eos_row, static_cast<size_t>(max_seqs) * 4));
+  CK(cudaMalloc(&e->pfx, static_cast<size_t>(max_seqs) * 4));
+  CK(cudaMalloc(&e->own_len, static_cast<size_t>(max_seqs) * 4));
+  CK(cudaMalloc(&e->meta, static_cast<size_t>(max_seqs) * 16));
   CK(cudaMalloc(&e->total_rows, 4));
   CK(cudaMemset(e->total_rows, 0, 4));
   e->max_seqs = max_seqs;
@@ -342,13 +347,13 @@ extern "C" int leaf_reserve(leaf_handle_t e, int32_t max_seqs) {
 
 extern "C" int leaf_expand_tokenize(leaf_handle_t e, const uint8_t* caps, const int32_t* cap_off, int32_t B, int32_t n,
                                     const int32_t* pos, const int32_t* chr, const int32_t* sel, const uint8_t* valid,
-                                    int32_t* tok_out, int32_t* len_out, int32_t* status_out, void* stream) {
+                                    int32_t* tok_out, int32_t* len_out, int32_t* base_out, int32_t* status_out, void* stream) {
   if (!e || !caps || !cap_off || !tok_out || !len_out) return fail(LEAF_ERR_INVALID, "null argument");
   if (!e->bpe_loaded) return fail(LEAF_ERR_STATE, "leaf_load_bpe has not been called");
   if (B <= 0 || n < 0) return fail(LEAF_ERR_INVALID, "B=%d n=%d", B, n);
   if (n > 0 && (!pos || !chr)) return fail(LEAF_ERR_INVALID, "pos/chr required when n > 0");
-  K1Args a{caps, cap_off, B, n, pos, chr, sel, valid, tok_out, len_out, status_out};
-  const long R = static_cast<long>(B) * (n > 0 ? n : 1);
+  K1Args a{caps, cap_off, B, n, pos, chr, sel, valid, tok_out, len_out, base_out, status_out};
+  const long R = static_cast<long>(B) * (n > 0 ? n : 1) + (n > 0 ? B : 0);
   const int grid = static_cast<int>((R + K1_WARPS_PER_CTA - 1) / K1_WARPS_PER_CTA);
   k1_expand_tokenize_kernel<<<grid, K1_WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(e->tables, a);
   e->launches++;
@@ -377,8 +382,8 @@ static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev,
   return LEAF_OK;
 }
 
-extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* len, int32_t N, int32_t normalize,
-                           float* feat_out, void* stream) {
+extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* len, const int32_t* base, int32_t N,
+                           int32_t normalize, float* feat_out, void* stream) {
   if (!e || !tok || !len || !feat_out) return fail(LEAF_ERR_INVALID, "null argument");
   if (!e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
   if (N <= 0) return fail(LEAF_ERR_INVALID, "N=%d", N);
@@ -387,16 +392,18 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
   const int W = e->cfg.width, E = e->cfg.embed_dim, H = e->cfg.heads;
   const int rows_max = static_cast<int>(static_cast<long>(N) * LEAF_CTX);
   int rc;
-  scan_lengths_kernel<<<1, 1024, 0, st>>>(len, N, e->cu, e->total_rows);
-  embed_kernel<<<N, 256, 0, st>>>(tok, e->cu, N, W, e->wp.token_embedding, e->wp.positional_embedding, e->x);
-  e->launches += 2;
+  prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, base, N, e->pfx, e->own_len);
+  scan_lengths_kernel<<<1, 1024, 0, st>>>(e->own_len, N, e->cu, e->total_rows);
+  meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(e->cu, e->pfx, base, N, e->meta, e->eos_row);
+  embed_kernel<<<N, 256, 0, st>>>(tok, e->meta, N, W, e->wp.token_embedding, e->wp.positional_embedding, e->x);
+  e->launches += 4;
   CK(cudaGetLastError());
   for (int l = 0; l < e->cfg.layers; ++l) {
     const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
     const LayerW& w = e->lw[l];
     if ((rc = launch_layernorm(e, e->x, e->total_rows, rows_max, nullptr, p.ln1_w, p.ln1_b, e->h, st))) return rc;
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.qkv_w, w.qkv_b, e->big, 3 * W, rows_max, 3 * W, W, EPI_BF16, 0, e->total_rows, st))) return rc;
-    attention_kernel<<<dim3(N, H), 96, 0, st>>>(e->big, e->cu, W, e->h);
+    attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(e->big, e->meta, N, H, W, e->h);
     e->launches++;
     CK(cudaGetLastError());
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.out_w, p.out_b, e->x, W, rows_max, W, W, EPI_F32_RESIDUAL, 0, e->total_rows, st))) return rc;
@@ -404,8 +411,6 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.fc1_w, p.fc1_b, e->big, 4 * W, rows_max, 4 * W, W, EPI_BF16_ACT, e->cfg.activation, e->total_rows, st))) return rc;
     if ((rc = launch_gemm(e, e->big, e->rows_cap, w.fc2_w, p.fc2_b, e->x, W, rows_max, W, 4 * W, EPI_F32_RESIDUAL, 0, e->total_rows, st))) return rc;
   }
-  eos_rows_kernel<<<(N + 255) / 256, 256, 0, st>>>(e->cu, N, e->eos_row);
-  e->launches++;
   if ((rc = launch_layernorm(e, e->x, nullptr, N, e->eos_row, e->wp.lnf_w, e->wp.lnf_b, e->pooled, st))) return rc;
   if ((rc = launch_gemm(e, e->pooled, e->max_seqs + 128, e->proj_w, nullptr, feat_out, E, N, E, W, EPI_F32, 0, nullptr, st))) return rc;
   if (normalize) {
@@ -442,10 +447,12 @@ extern "C" int leaf_test_layernorm(leaf_handle_t e, const float* x, int32_t rows
   return launch_layernorm(e, x, nullptr, rows, nullptr, gamma, beta, static_cast<__nv_bfloat16*>(y), static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int leaf_test_attention(leaf_handle_t e, const void* qkv, const int32_t* cu, int32_t N, void* out, void* stream) {
-  if (!e || !qkv || !cu || !out || N <= 0) return fail(LEAF_ERR_INVALID, "bad argument");
-  attention_kernel<<<dim3(N, e->cfg.heads), 96, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), cu, e->cfg.width, static_cast<__nv_bfloat16*>(out));
+extern "C" int leaf_test_attention(leaf_handle_t e, const void* qkv, const int32_t* meta, int32_t N, void* out, void* stream) {
+  if (!e || !qkv || !meta || !out || N <= 0) return fail(LEAF_ERR_INVALID, "bad argument");
+  const int H = e->cfg.heads;
+  attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const int4*>(meta), N, H, e->cfg.width,
+      static_cast<__nv_bfloat16*>(out));
   e->launches++;
   CK(cudaGetLastError());
   return LEAF_OK;

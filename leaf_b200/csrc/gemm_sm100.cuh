@@ -140,9 +140,37 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// nn.GELU (erf form): 0.5 x (1 + erf(x / sqrt 2)). erfc(z) = poly(t) exp(-z^2), t = 1/(1 + p z) (Abramowitz-Stegun
+// 7.1.26, |error| <= 1.5e-7 on erf), evaluated on |x| so that the negative tail has no cancellation. ~14 FP32 ops
+// + 2 MUFU per element: libdevice's erff costs ~39 instructions and made the fc1 epilogue the bottleneck (profiles/).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(t, poly, 1.421413741f);
+  poly = fmaf(t, poly, -0.284496736f);
+  poly = fmaf(t, poly, 0.254829592f);
+  poly *= t;
+  const float e = fast_ex2(x * x * -0.72134752044448170368f);            // exp(-x^2 / 2)
+  const float h = 0.5f * x * poly * e;                                   // 0.5 x erfc(|x| / sqrt 2)
+  return x >= 0.f ? x - h : h;
+}
 __device__ __forceinline__ float act_apply(float x, int act) {
-  if (act == ACT_QUICK_GELU) return x / (1.0f + __expf(-1.702f * x));   // x * sigmoid(1.702 x)
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));          // nn.GELU (erf)
+  if (act == ACT_QUICK_GELU) return x * fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));   // x sigmoid(1.702 x)
+  return gelu_erf(x);
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -250,8 +278,23 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     const int half = (warp - 4) >> 2;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // residual epilogue: the fp32 tile it will read-modify-write is pulled into L2 one tile ahead, while the MMAs of
+    // that tile are still running (the out-proj GEMM sits at the HBM/tensor ridge, profiles/r1)
+    auto prefetch_residual = [&](int tile) {
+      if (EPI != EPI_F32_RESIDUAL || tile >= total_tiles) return;
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int row = m_blk * GEMM_BM + quad * 32 + lane;
+      if (row >= M) return;
+      const int col0 = n_blk * GEMM_BN + half * (GEMM_BN / 2);
+      const float* r = reinterpret_cast<const float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+#pragma unroll
+      for (int c = 0; c < GEMM_BN / 2; c += 32)
+        if (col0 + c < p.N) prefetch_l2(r + c);
+    };
+    prefetch_residual(blockIdx.x);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      prefetch_residual(tile + gridDim.x);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row = m_blk * GEMM_BM + quad * 32 + lane;

@@ -25,6 +25,7 @@ struct K1Args {
   const uint8_t* valid;
   int32_t* tok_out;
   int32_t* len_out;
+  int32_t* base_out;      // [R] index of the row holding the sample's unedited caption, -1 for those rows
   int32_t* status_out;
 };
 
@@ -41,10 +42,12 @@ __global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32) k1_expand_tokenize_kern
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = a.n > 0 ? a.n : 1;
-  const int R = a.B * per;
+  const int n_cand = a.B * per;
+  const int R = n_cand + (a.n > 0 ? a.B : 0);          // candidates, then (n > 0) the B unedited captions
   const int r = blockIdx.x * K1_WARPS_PER_CTA + w;
   if (r >= R) return;
-  const int b = r / per;
+  const bool is_base = r >= n_cand;
+  const int b = is_base ? r - n_cand : r / per;
   const int off = a.cap_off[b];
   int len = a.cap_off[b + 1] - off;
   int flags = 0;
@@ -60,9 +63,9 @@ __global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32) k1_expand_tokenize_kern
 
   K1Scratch S{s_a[w], s_b[w], s_sym[w], s_rk[w], s_ps[w], s_pl[w], 0, 0};
   if (lane == 0) {
-    bool edit = a.n > 0 && (!a.valid || a.valid[r]);
+    bool edit = a.n > 0 && !is_base && (!a.valid || a.valid[r]);
     int z = 0, c = -1;
-    if (a.n > 0) {
+    if (a.n > 0 && !is_base) {
       z = a.sel ? a.pos[b * a.n + a.sel[b]] : a.pos[r];
       c = a.chr[r];
       if (z < 0 || z > 2 * len) { edit = false; flags |= K1_FLAG_TOO_LONG; }
@@ -83,7 +86,10 @@ __global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32) k1_expand_tokenize_kern
   __syncwarp();
   int32_t* out = a.tok_out + static_cast<size_t>(r) * K1_CTX;
   for (int i = lane; i < K1_CTX; i += 32) out[i] = s_row[w][i];
-  if (lane == 0) a.len_out[r] = s_meta[w][2];
+  if (lane == 0) {
+    a.len_out[r] = s_meta[w][2];
+    if (a.base_out) a.base_out[r] = (a.n > 0 && !is_base) ? n_cand + b : -1;
+  }
 }
 
 }  // namespace leaf

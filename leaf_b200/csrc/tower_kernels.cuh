@@ -64,21 +64,61 @@ __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// shared-prefix analysis. Row i may name a base row base[i] of the same batch (the unedited caption of its
+// sample): hidden states of the positions where both token rows agree are identical under the causal mask, so only
+// positions [p, t) of row i are computed and its attention reads the base's keys/values for [0, p).
+// own_len[i] = t - p with p = min(common prefix, t - 1) (the pooled EOS row is always computed). One warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) prefix_kernel(const int* __restrict__ tok, const int* __restrict__ len,
+                                                     const int* __restrict__ base, int N, int* __restrict__ pfx,
+                                                     int* __restrict__ own_len) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= N) return;
+  const int t = min(max(len[i], 1), 77);
+  int p = 0;
+  const int b = base ? base[i] : -1;
+  if (b >= 0 && b < N && b != i) {
+    const int tb = min(max(len[b], 1), 77);
+    const int lim = min(t, tb);
+    p = lim;
+    for (int c = 0; c < 96; c += 32) {
+      const int k = c + lane;
+      const bool diff = (k < lim) && (tok[i * 77 + k] != tok[b * 77 + k]);
+      const unsigned m = __ballot_sync(0xffffffffu, diff);
+      if (m) { p = c + __ffs(m) - 1; break; }
+    }
+    p = min(p, t - 1);
+  }
+  if (lane == 0) { pfx[i] = p; own_len[i] = t - p; }
+}
+
+// meta[i] = {own_row, t, p, base_row}; eos_row[i] = last own row
+__global__ void meta_kernel(const int* __restrict__ cu, const int* __restrict__ pfx, const int* __restrict__ base, int N,
+                            int4* __restrict__ meta, int* __restrict__ eos_row) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int own = cu[i], n_own = cu[i + 1] - own, p = pfx[i];
+  const int b = (base && p > 0) ? base[i] : i;
+  meta[i] = make_int4(own, p + n_own, p, cu[b]);
+  eos_row[i] = own + n_own - 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // x[row,:] = token_embedding[id] + positional_embedding[pos]      (model.py:272-274), fp32
 // one warp per packed row; grid = sequences
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) embed_kernel(const int* __restrict__ tok, const int* __restrict__ cu, int N, int W,
+__global__ void __launch_bounds__(256) embed_kernel(const int* __restrict__ tok, const int4* __restrict__ meta, int N, int W,
                                                     const float* __restrict__ tok_emb, const float* __restrict__ pos_emb,
                                                     float* __restrict__ x) {
   const int seq = blockIdx.x;
   if (seq >= N) return;
-  const int start = cu[seq], t = cu[seq + 1] - start;
+  const int4 mt = meta[seq];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
-  for (int pos = warp; pos < t; pos += nwarp) {
+  for (int pos = mt.z + warp; pos < mt.y; pos += nwarp) {
     const int id = tok[seq * 77 + pos];
     const float4* e = reinterpret_cast<const float4*>(tok_emb + static_cast<size_t>(id) * W);
     const float4* pe = reinterpret_cast<const float4*>(pos_emb + static_cast<size_t>(pos) * W);
-    float4* o = reinterpret_cast<float4*>(x + static_cast<size_t>(start + pos) * W);
+    float4* o = reinterpret_cast<float4*>(x + static_cast<size_t>(mt.x + pos - mt.z) * W);
     for (int c = lane; c < W / 4; c += 32) {
       float4 a = __ldg(e + c), b = __ldg(pe + c);
       o[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
@@ -132,87 +172,162 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
   }
 }
 
-// pooled row index of every sequence: cu[i] + len[i] - 1
-__global__ void eos_rows_kernel(const int* __restrict__ cu, int N, int* __restrict__ eos_row) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) eos_row[i] = cu[i + 1] - 1;
-}
-
 // ---------------------------------------------------------------------------------------------
 // causal attention over packed rows, head_dim 64 (nn.MultiheadAttention with the additive -inf mask,
-// transformer.py:225,250-252,758-764; scale 1/sqrt(64)). One CTA per (sequence, head); K and V of the
-// sequence staged in shared memory as fp32; one thread per query row with an online softmax in fp32.
+// transformer.py:225,250-252,758-764; scale 1/sqrt(64)).
+//
+// One warp per (sequence, head); everything stays in registers: mma.sync.m16n8k16 (bf16, fp32 accumulate) for
+// Q.K^T and P.V, online softmax in fp32 (exp2 with the scale folded in). Operand fragments are read straight from
+// global memory with 16-byte loads: the contraction index of Q.K^T is permuted identically for Q and K so that a
+// lane's 8 contiguous bf16 feed two k-steps, and V fragments are transposed in registers with movmatrix, which
+// leaves every lane with 8 contiguous output columns (one 16-byte store per row and 32-column block).
+// tcgen05's 128-row tiles do not fit 2..77-row problems (1.2 % of the tower's FLOPs); this kernel is bandwidth bound.
+//
+// meta[seq] = {own_row, t, p, base_row}: the sequence has t positions; positions [p, t) are its own packed rows
+// starting at own_row (they are the queries); keys/values of positions [0, p) are read from the rows of another
+// sequence starting at base_row (shared prefix under the causal mask), p = 0 when nothing is shared.
 // qkv: bf16 [rows, 3W] (q | k | v), out: bf16 [rows, W].
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(96) attention_kernel(const __nv_bfloat16* __restrict__ qkv, const int* __restrict__ cu,
-                                                       int W, __nv_bfloat16* __restrict__ out) {
-  __shared__ float Ks[77][64];
-  __shared__ float Vs[77][64];
-  const int seq = blockIdx.x, head = blockIdx.y;
-  const int start = cu[seq], t = cu[seq + 1] - start;
+constexpr int ATT_WARPS = 4;
+
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t movmatrix_trans(uint32_t x) {
+  uint32_t y;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__global__ void __launch_bounds__(ATT_WARPS * 32) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
+                                                                    const int4* __restrict__ meta, int n_seq, int heads,
+                                                                    int W, __nv_bfloat16* __restrict__ out) {
+  const int pair = blockIdx.x * ATT_WARPS + (threadIdx.x >> 5);
+  if (pair >= n_seq * heads) return;
+  const int seq = pair / heads, head = pair - seq * heads;
+  const int lane = threadIdx.x & 31, g = lane >> 2, c = lane & 3;
+  const int4 mt = __ldg(meta + seq);
+  const int own_row = mt.x, t = mt.y, p = mt.z, base_row = mt.w;
+  const int nq = t - p;
   const size_t ld = static_cast<size_t>(3) * W;
-  // stage K, V: 8 bf16 (16 B) per thread-iteration
-  for (int idx = threadIdx.x; idx < t * 8; idx += blockDim.x) {
-    const int r = idx >> 3, c8 = (idx & 7) * 8;
-    const __nv_bfloat16* base = qkv + (static_cast<size_t>(start + r)) * ld + head * 64 + c8;
-    const uint4 kk = *reinterpret_cast<const uint4*>(base + W);
-    const uint4 vv = *reinterpret_cast<const uint4*>(base + 2 * W);
-    const __nv_bfloat162* kp = reinterpret_cast<const __nv_bfloat162*>(&kk);
-    const __nv_bfloat162* vp = reinterpret_cast<const __nv_bfloat162*>(&vv);
+  const __nv_bfloat16* qbase = qkv + head * 64 + c * 8;
+  const __nv_bfloat16* kbase = qbase + W;
+  const __nv_bfloat16* vbase = qbase + 2 * W;
+  const float sl2 = 0.125f * 1.4426950408889634f;          // 1/sqrt(64) * log2(e)
+  auto key_row = [&](int j) -> size_t {                     // packed row that holds position j of this sequence
+    j = min(j, t - 1);
+    return static_cast<size_t>(j < p ? base_row + j : own_row + (j - p));
+  };
+  for (int q0 = 0; q0 < nq; q0 += 16) {
+    // ---- Q fragments: rows q0+g and q0+g+8, two 32-wide d blocks, 8 contiguous bf16 per lane and block ----
+    const int qi0 = min(q0 + g, nq - 1), qi1 = min(q0 + g + 8, nq - 1);
+    uint32_t qf[2][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 kf = __bfloat1622float2(kp[j]);
-      const float2 vf = __bfloat1622float2(vp[j]);
-      Ks[r][c8 + 2 * j] = kf.x; Ks[r][c8 + 2 * j + 1] = kf.y;
-      Vs[r][c8 + 2 * j] = vf.x; Vs[r][c8 + 2 * j + 1] = vf.y;
+    for (int b = 0; b < 2; ++b) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(qbase + (static_cast<size_t>(own_row + qi0)) * ld + b * 32);
+      const uint4 r1 = *reinterpret_cast<const uint4*>(qbase + (static_cast<size_t>(own_row + qi1)) * ld + b * 32);
+      qf[b][0] = r0.x; qf[b][1] = r0.y; qf[b][2] = r0.z; qf[b][3] = r0.w;
+      qf[b][4] = r1.x; qf[b][5] = r1.y; qf[b][6] = r1.z; qf[b][7] = r1.w;
     }
-  }
-  __syncthreads();
-  const int i = threadIdx.x;
-  if (i >= t) return;
-  float q[64], o[64];
-  {
-    const __nv_bfloat16* qp = qkv + (static_cast<size_t>(start + i)) * ld + head * 64;
+    const int pos0 = p + qi0, pos1 = p + qi1;               // absolute positions of the two query rows
+    float o[8][4];
 #pragma unroll
-    for (int c = 0; c < 64; c += 8) {
-      const uint4 qq = *reinterpret_cast<const uint4*>(qp + c);
-      const __nv_bfloat162* q2 = reinterpret_cast<const __nv_bfloat162*>(&qq);
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    const int kmax = min(t - 1, p + q0 + 15);
+    for (int j0 = 0; j0 <= kmax; j0 += 16) {
+      // ---- S = Q.K^T for 16 keys (two n-tiles of 8) ----
+      float s[2][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __bfloat1622float2(q2[j]);
-        q[c + 2 * j] = f.x * 0.125f; q[c + 2 * j + 1] = f.y * 0.125f;
+      for (int nt = 0; nt < 2; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const size_t kr = key_row(j0 + nt * 8 + g);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const uint4 kk = *reinterpret_cast<const uint4*>(kbase + kr * ld + b * 32);
+          const uint32_t a_lo[4] = {qf[b][0], qf[b][4], qf[b][1], qf[b][5]};
+          const uint32_t a_hi[4] = {qf[b][2], qf[b][6], qf[b][3], qf[b][7]};
+          mma_bf16_16816(s[nt], a_lo, kk.x, kk.y);
+          mma_bf16_16816(s[nt], a_hi, kk.z, kk.w);
+        }
+      }
+      // ---- causal mask + online softmax (rows g and g+8 live on the 4 lanes of a quad) ----
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = j0 + nt * 8 + 2 * c + e;
+          if (j > pos0) s[nt][e] = -INFINITY;
+          if (j > pos1) s[nt][2 + e] = -INFINITY;
+          mx0 = fmaxf(mx0, s[nt][e]);
+          mx1 = fmaxf(mx1, s[nt][2 + e]);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);      // finite: key 0 is visible to every query
+      const float corr0 = exp2f((m0 - mn0) * sl2), corr1 = exp2f((m1 - mn1) * sl2);
+      m0 = mn0; m1 = mn1;
+      float ps0 = 0.f, ps1 = 0.f;
+      uint32_t pf[4];
+#pragma unroll
+      for (int nt = 0; nt < 2; ++nt) {
+        const float p00 = exp2f((s[nt][0] - mn0) * sl2), p01 = exp2f((s[nt][1] - mn0) * sl2);
+        const float p10 = exp2f((s[nt][2] - mn1) * sl2), p11 = exp2f((s[nt][3] - mn1) * sl2);
+        ps0 += p00 + p01;
+        ps1 += p10 + p11;
+        pf[2 * nt] = pack_bf16x2(p00, p01);
+        pf[2 * nt + 1] = pack_bf16x2(p10, p11);
+      }
+      l0 = l0 * corr0 + ps0;
+      l1 = l1 * corr1 + ps1;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i][0] *= corr0; o[i][1] *= corr0; o[i][2] *= corr1; o[i][3] *= corr1;
+      }
+      // ---- O += P.V : V fragments transposed in registers ----
+      const size_t vr0 = key_row(j0 + g), vr1 = key_row(j0 + 8 + g);
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(vbase + vr0 * ld + b * 32);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(vbase + vr1 * ld + b * 32);
+        const uint32_t v0r[4] = {v0.x, v0.y, v0.z, v0.w}, v1r[4] = {v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          mma_bf16_16816(o[b * 4 + i], pf, movmatrix_trans(v0r[i]), movmatrix_trans(v1r[i]));
       }
     }
-  }
+    // ---- normalise and store: lane holds columns 32b + 8c .. + 7 of rows g and g+8 ----
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.f / l0, inv1 = 1.f / l1;
 #pragma unroll
-  for (int c = 0; c < 64; ++c) o[c] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  for (int j = 0; j <= i; ++j) {
-    float s = 0.f;
-#pragma unroll
-    for (int c = 0; c < 64; ++c) s = fmaf(q[c], Ks[j][c], s);
-    const float mn = fmaxf(m, s);
-    const float corr = __expf(m - mn);
-    const float pj = __expf(s - mn);
-    l = l * corr + pj;
-#pragma unroll
-    for (int c = 0; c < 64; ++c) o[c] = fmaf(o[c], corr, pj * Vs[j][c]);
-    m = mn;
-  }
-  const float inv = 1.f / l;
-  __nv_bfloat16* op = out + (static_cast<size_t>(start + i)) * W + head * 64;
-#pragma unroll
-  for (int c = 0; c < 64; c += 8) {
-    uint4 pk;
-    __nv_bfloat162 t0 = __floats2bfloat162_rn(o[c] * inv, o[c + 1] * inv);
-    __nv_bfloat162 t1 = __floats2bfloat162_rn(o[c + 2] * inv, o[c + 3] * inv);
-    __nv_bfloat162 t2 = __floats2bfloat162_rn(o[c + 4] * inv, o[c + 5] * inv);
-    __nv_bfloat162 t3 = __floats2bfloat162_rn(o[c + 6] * inv, o[c + 7] * inv);
-    pk.x = *reinterpret_cast<uint32_t*>(&t0);
-    pk.y = *reinterpret_cast<uint32_t*>(&t1);
-    pk.z = *reinterpret_cast<uint32_t*>(&t2);
-    pk.w = *reinterpret_cast<uint32_t*>(&t3);
-    *reinterpret_cast<uint4*>(op + c) = pk;
+    for (int b = 0; b < 2; ++b) {
+      uint4 w0, w1;
+      w0.x = pack_bf16x2(o[b * 4 + 0][0] * inv0, o[b * 4 + 0][1] * inv0);
+      w0.y = pack_bf16x2(o[b * 4 + 1][0] * inv0, o[b * 4 + 1][1] * inv0);
+      w0.z = pack_bf16x2(o[b * 4 + 2][0] * inv0, o[b * 4 + 2][1] * inv0);
+      w0.w = pack_bf16x2(o[b * 4 + 3][0] * inv0, o[b * 4 + 3][1] * inv0);
+      w1.x = pack_bf16x2(o[b * 4 + 0][2] * inv1, o[b * 4 + 0][3] * inv1);
+      w1.y = pack_bf16x2(o[b * 4 + 1][2] * inv1, o[b * 4 + 1][3] * inv1);
+      w1.z = pack_bf16x2(o[b * 4 + 2][2] * inv1, o[b * 4 + 2][3] * inv1);
+      w1.w = pack_bf16x2(o[b * 4 + 3][2] * inv1, o[b * 4 + 3][3] * inv1);
+      __nv_bfloat16* ob = out + head * 64 + b * 32 + c * 8;
+      if (q0 + g < nq) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(own_row + q0 + g) * W) = w0;
+      if (q0 + g + 8 < nq) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(own_row + q0 + g + 8) * W) = w1;
+    }
   }
 }
 

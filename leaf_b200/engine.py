@@ -182,14 +182,17 @@ class LeafEngine:
         return d, o
 
     def expand_tokenize(self, caps_dev, off_dev, B, n, pos=None, chr_=None, sel=None, valid=None):
-        """leaf_expand_tokenize on device tensors; returns (tokens int32 [R,77], lengths int32 [R])."""
-        R = B * max(n, 1)
+        """leaf_expand_tokenize on device tensors; returns (tokens int32 [R,77], lengths int32 [R], base int32 [R]).
+        n == 0: R = B (the captions). n > 0: R = B*n + B, the candidates followed by the B unedited captions; base[r]
+        names the caption row of candidate r (shared-prefix reuse in encode_tokens), -1 for the caption rows."""
+        R = B * n + B if n > 0 else B
         tok = torch.empty((R, CONTEXT_LENGTH), dtype=torch.int32, device=self.device)
         ln = torch.empty((R,), dtype=torch.int32, device=self.device)
+        base = torch.empty((R,), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             check(self._lib.leaf_expand_tokenize(self._h, _ptr(caps_dev), _ptr(off_dev), B, n, _ptr(pos), _ptr(chr_), _ptr(sel),
-                                                 _ptr(valid), _ptr(tok), _ptr(ln), _ptr(self._status), _stream()))
-        return tok, ln
+                                                 _ptr(valid), _ptr(tok), _ptr(ln), _ptr(base), _ptr(self._status), _stream()))
+        return tok, ln, base
 
     def check_status(self):
         """Synchronising read of the tokenizer status flags; raises on inputs outside the kernel's closed domain."""
@@ -205,14 +208,16 @@ class LeafEngine:
         if isinstance(texts, str):
             texts = [texts]
         d, o = self.upload_captions(texts)
-        tok, _ = self.expand_tokenize(d, o, len(texts), 0)
+        tok, _, _ = self.expand_tokenize(d, o, len(texts), 0)
         if check:
             self.check_status()
         return tok.long()
 
     # ---- K2 ----------------------------------------------------------------------------------------------
-    def encode_tokens(self, tok: torch.Tensor, lengths: torch.Tensor = None, normalize: bool = False) -> torch.Tensor:
-        """CLIP.encode_text (model.py:269-284) for token rows already on the device."""
+    def encode_tokens(self, tok: torch.Tensor, lengths: torch.Tensor = None, normalize: bool = False,
+                      base: torch.Tensor = None) -> torch.Tensor:
+        """CLIP.encode_text (model.py:269-284) for token rows already on the device. `base` (int32 [N], -1 = none)
+        names for each row another row of the batch it shares a token prefix with (computed once, results identical)."""
         if tok.dtype != torch.int32:
             tok = tok.to(torch.int32)
         tok = tok.contiguous()
@@ -222,7 +227,8 @@ class LeafEngine:
         self.reserve(N)
         out = torch.empty((N, self.embed_dim), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(self._lib.leaf_encode(self._h, _ptr(tok), _ptr(lengths.contiguous()), N, 1 if normalize else 0, _ptr(out), _stream()))
+            check(self._lib.leaf_encode(self._h, _ptr(tok), _ptr(lengths.contiguous()), _ptr(base), N, 1 if normalize else 0,
+                                        _ptr(out), _stream()))
         return out
 
     # ---- K3 ----------------------------------------------------------------------------------------------
@@ -251,9 +257,10 @@ class LeafEngine:
         check(self._lib.leaf_test_layernorm(self._h, _ptr(x), x.shape[0], _ptr(gamma), _ptr(beta), _ptr(y), _stream()))
         return y
 
-    def test_attention(self, qkv, cu):
-        out = torch.empty((qkv.shape[0], self.width), dtype=torch.bfloat16, device=qkv.device)
-        check(self._lib.leaf_test_attention(self._h, _ptr(qkv), _ptr(cu), cu.shape[0] - 1, _ptr(out), _stream()))
+    def test_attention(self, qkv, meta):
+        """meta int32 [N,4] = {own_row, t, p, base_row} per sequence."""
+        out = torch.zeros((qkv.shape[0], self.width), dtype=torch.bfloat16, device=qkv.device)
+        check(self._lib.leaf_test_attention(self._h, _ptr(qkv), _ptr(meta), meta.shape[0], _ptr(out), _stream()))
         return out
 
     def launch_count(self, reset=False) -> int:

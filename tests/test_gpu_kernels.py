@@ -81,18 +81,34 @@ def test_layernorm(eng):
 def test_attention_varlen_causal(eng):
     g = torch.Generator(device="cuda").manual_seed(2)
     W, H = eng.width, eng.heads
-    lens = [1, 2, 13, 77, 40, 5, 77, 3]
-    cu = torch.tensor(np.concatenate([[0], np.cumsum(lens)]), dtype=torch.int32, device="cuda")
+    lens = [1, 2, 13, 77, 40, 5, 77, 3, 16, 17, 33]
+    cu = np.concatenate([[0], np.cumsum(lens)])
     rows = int(cu[-1])
     qkv = torch.randn((rows, 3 * W), generator=g, device="cuda").to(torch.bfloat16)
-    out = eng.test_attention(qkv, cu).float()
+    meta = torch.tensor([[cu[i], t, 0, cu[i]] for i, t in enumerate(lens)], dtype=torch.int32, device="cuda")
+    out = eng.test_attention(qkv, meta).float()
+
+    def ref_attn(q, k, v, first_q):
+        t, nq = k.shape[0], q.shape[0]
+        q, k, v = (z.float().view(-1, H, 64).transpose(0, 1) for z in (q, k, v))
+        mask = torch.full((nq, t), float("-inf"), device="cuda").triu_(1 + first_q)
+        return (torch.softmax((q @ k.transpose(-1, -2)) * 0.125 + mask, -1) @ v).transpose(0, 1).reshape(nq, W)
+
     for i, t in enumerate(lens):
         s = int(cu[i])
-        q, k, v = qkv[s:s + t].float().split(W, dim=-1)
-        q, k, v = (z.view(t, H, 64).transpose(0, 1) for z in (q, k, v))
-        att = (q @ k.transpose(-1, -2)) * 0.125 + torch.full((t, t), float("-inf"), device="cuda").triu_(1)
-        ref = (torch.softmax(att, -1) @ v).transpose(0, 1).reshape(t, W)
-        assert torch.allclose(out[s:s + t], ref, atol=2e-2, rtol=1e-2), i
+        q, k, v = qkv[s:s + t].split(W, dim=-1)
+        # tolerance: P is rounded to bf16 before P.V, and the output is stored in bf16
+        assert torch.allclose(out[s:s + t], ref_attn(q, k, v, 0), atol=3e-2, rtol=2e-2), i
+    # shared prefix: sequence 1 (t = 50) owns positions [p, 50) only and reads positions [0, p) from sequence 0's rows
+    for p in (0, 1, 15, 16, 31, 49):
+        t0, t1 = 60, 50
+        own = t1 - p
+        qkv = torch.randn((t0 + own, 3 * W), generator=g, device="cuda").to(torch.bfloat16)
+        meta = torch.tensor([[0, t0, 0, 0], [t0, t1, p, 0]], dtype=torch.int32, device="cuda")
+        out = eng.test_attention(qkv, meta).float()
+        full = torch.cat([qkv[:p], qkv[t0:]])              # the sequence as if it had been computed alone
+        q, k, v = full.split(W, dim=-1)
+        assert torch.allclose(out[t0:], ref_attn(q[p:], k, v, p), atol=3e-2, rtol=2e-2), p
 
 
 def test_score_argmax(eng):
@@ -126,10 +142,16 @@ def test_score_argmax(eng):
 def _k1(eng, caps, n=0, pos=None, chr_=None, sel=None, valid=None):
     d, o = eng.upload_captions(caps)
     t = lambda a, dt: None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=dt).cuda()
-    tok, ln = eng.expand_tokenize(d, o, len(caps), n, t(pos, torch.int32), t(chr_, torch.int32), t(sel, torch.int32),
-                                  t(valid, torch.uint8))
+    tok, ln, base = eng.expand_tokenize(d, o, len(caps), n, t(pos, torch.int32), t(chr_, torch.int32), t(sel, torch.int32),
+                                        t(valid, torch.uint8))
     torch.cuda.synchronize()
-    return tok.cpu().numpy(), ln.cpu().numpy()
+    R = len(caps) * max(n, 1)
+    if n > 0:      # the B unedited captions follow the candidates, and every candidate names its caption row
+        from oracle import leaf_oracle as O
+        assert tok.shape[0] == R + len(caps)
+        assert torch.equal(tok[R:].cpu().long(), O.OracleTokenizer()(list(caps)))
+        assert base[:R].cpu().tolist() == [R + r // n for r in range(R)] and (base[R:] == -1).all()
+    return tok[:R].cpu().numpy(), ln[:R].cpu().numpy()
 
 
 def test_k1_golden_strings(eng, golden_dir):

@@ -91,6 +91,27 @@ def test_tower_row_position_invariance():
     assert torch.equal(f[40:47], f[:7]) and torch.equal(f[48:52], f[5:9])
 
 
+def test_shared_prefix_is_bit_identical():
+    """Encoding candidates with shared-prefix reuse (base rows) must equal encoding every row on its own."""
+    from leaf_b200 import synth
+    from leaf_b200.tower import LeafTextTower
+    tower = LeafTextTower.random("small", seed=8)
+    eng = tower.leaf_engine
+    B, n = 12, 40
+    caps = synth.make_captions(B - 2, seed=4) + synth.make_captions(2, seed=4, kind="dense-77")
+    rng = np.random.RandomState(1)
+    pos = np.stack([rng.randint(0, 2 * len(S) + 1, size=n) for S in caps]).astype(np.int32)
+    chr_ = np.array(synth.V_DEFAULT, dtype=np.int32)[rng.randint(0, 96, size=(B, n))]
+    d, o = eng.upload_captions(caps)
+    tok, ln, base = eng.expand_tokenize(d, o, B, n, torch.from_numpy(pos).cuda(), torch.from_numpy(chr_).cuda())
+    shared = eng.encode_tokens(tok, ln, False, base)
+    rows_shared = eng.last_rows()
+    plain = eng.encode_tokens(tok, ln, False, None)
+    rows_plain = eng.last_rows()
+    assert torch.equal(shared, plain)
+    assert rows_plain == int(ln.sum()) and rows_shared < 0.75 * rows_plain
+
+
 def _golden_attack(golden_dir):
     from leaf_b200 import synth
     g = json.load(open(os.path.join(golden_dir, "attack_golden.json")))
@@ -162,11 +183,11 @@ def test_attack_full_config_vs_oracle_scores():
     want_feats = O.encode_text(sd, otok(strings), cfg.heads)
     want_loss = O.score(want_feats.view(B, n, -1), anchor)
     d, o = eng.upload_captions(caps)
-    tok, ln = eng.expand_tokenize(d, o, B, n, torch.from_numpy(pos).cuda(), torch.full((B * n,), 32, dtype=torch.int32).cuda())
-    assert torch.equal(tok.cpu().long(), otok(strings))
-    feats = eng.encode_tokens(tok, ln)
+    tok, ln, base = eng.expand_tokenize(d, o, B, n, torch.from_numpy(pos).cuda(), torch.full((B * n,), 32, dtype=torch.int32).cuda())
+    assert torch.equal(tok[:B * n].cpu().long(), otok(strings))
+    feats = eng.encode_tokens(tok, ln, False, base)
     best, bf, loss = eng.score(feats, anchor.cuda(), B, n, "l2", want_loss=True)
-    assert _cos(feats.cpu(), want_feats).min() >= COS_MIN
+    assert _cos(feats[:B * n].cpu(), want_feats).min() >= COS_MIN
     rel = ((loss.cpu() - want_loss).abs() / want_loss.abs().clamp_min(1e-12))
     assert rel.max() <= LOSS_RTOL, rel.max().item()
     top = torch.topk(want_loss, 2, dim=-1).values

@@ -28,11 +28,11 @@ d, o = eng.upload_captions(caps)
 
 
 def step():
-    tok, ln = eng.expand_tokenize(d, o, B, n, pos=pos, chr_=space)
-    f = eng.encode_tokens(tok, ln)
+    tok, ln, base = eng.expand_tokenize(d, o, B, n, pos=pos, chr_=space)
+    f = eng.encode_tokens(tok, ln, False, base)
     best1, _, _ = eng.score(f, anchor, B, n, "l2")
-    tok, ln = eng.expand_tokenize(d, o, B, n, pos=pos, chr_=ch, sel=best1)
-    f = eng.encode_tokens(tok, ln)
+    tok, ln, base = eng.expand_tokenize(d, o, B, n, pos=pos, chr_=ch, sel=best1)
+    f = eng.encode_tokens(tok, ln, False, base)
     return eng.score(f, anchor, B, n, "l2")
 
 
