@@ -1,0 +1,216 @@
+// CTA-pair (cta_group::2) version of the tower GEMM: two CTAs on the two SMs of a TPC compute one 256x256 tile.
+//
+// Why: with 128x256 tiles per SM the operand traffic is 48 KB per 4.2 MFLOP (85 FLOP/B); 148 SMs at tensor peak
+// would pull ~26 TB/s out of L2, more than twice what the L2 delivers, and ncu showed the 1-CTA kernel stuck near
+// 1.0-1.1 PFLOP/s (profiles/r1, r2). In a pair each CTA stages its own 128 rows of A and only HALF of the B tile
+// (128 of the 256 weight rows); tcgen05.mma.cta_group::2 (M256 N256 K16) reads both halves, so a CTA moves 32 KB per
+// 4.2 MFLOP (131 FLOP/B) and the ring holds 6 stages instead of 4.
+//
+// Protocol (per stage s; "leader" = CTA rank 0 of the pair):
+//   producers (warp 0 of BOTH CTAs) wait on their local empty[s], then TMA their A and B boxes into local smem with
+//     cp.async.bulk.tensor...cta_group::2, whose complete_tx lands on the LEADER's full[s]; the leader's producer
+//     arms full[s] with the bytes of both CTAs;
+//   the leader's MMA thread waits full[s], issues 4 MMAs, then tcgen05.commit...multicast::cluster arrives on empty[s]
+//     of both CTAs (and on tmem_full[acc] of both after the last k-block);
+//   epilogue warps of both CTAs drain their own 128 TMEM lanes and arrive (remotely for the peer) on the leader's
+//     tmem_empty[acc] (count 16).
+#pragma once
+#include "gemm_sm100.cuh"
+
+namespace leaf {
+
+constexpr int GEMM2_BM = 256;                 // per pair (128 per CTA)
+constexpr int GEMM2_STAGES = 6;
+constexpr uint32_t GEMM2_A_BYTES = 128 * GEMM_BK * 2;
+constexpr uint32_t GEMM2_B_BYTES = 128 * GEMM_BK * 2;
+constexpr uint32_t GEMM2_STAGE_BYTES = GEMM2_A_BYTES + GEMM2_B_BYTES;
+constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA rank 0 of a pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* tmap, uint32_t bar_leader, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_leader), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(static_cast<uint16_t>(3)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar_local) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_local & PEER_BIT_MASK) : "memory");
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + GEMM2_STAGES * GEMM2_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM2_STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM2_STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM2_STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * GEMM2_STAGES + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + GEMM2_STAGES * GEMM2_STAGE_BYTES + 8u * (2 * GEMM2_STAGES + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int M = p.m_dev ? min(*p.m_dev, p.M) : p.M;
+  const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM;
+  const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
+  const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < GEMM2_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);           // leader producer's arrive.expect_tx (peer's copy of the barrier is unused)
+      mbar_init(empty_bar(s), 1);          // one multicast commit from the leader's MMA thread
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);          // multicast commit
+      mbar_init(tempty_bar(s), 16);        // 8 epilogue warps of each CTA (leader's copy is the one waited on)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();                       // barriers of both CTAs initialised, TMEM allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * GEMM2_STAGE_BYTES;
+          const uint32_t sb = sa + GEMM2_A_BYTES;
+          const uint32_t fb = full_bar(stage) & PEER_BIT_MASK;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
+          tma_load_2d_2sm(sa, &tmap_a, fb, kb * GEMM_BK, m_blk * GEMM2_BM + static_cast<int>(rank) * 128);
+          tma_load_2d_2sm(sb, &tmap_b, fb, kb * GEMM_BK, n_blk * GEMM_BN + static_cast<int>(rank) * 128);
+          if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: one thread of the leader CTA =====
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(GEMM2_BM, GEMM_BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * GEMM_BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * GEMM2_STAGE_BYTES;
+          const uint32_t sb = sa + GEMM2_A_BYTES;
+          const uint64_t adesc = make_smem_desc_sw128(sa);
+          const uint64_t bdesc = make_smem_desc_sw128(sb);
+#pragma unroll
+          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
+            umma_bf16_2sm(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(empty_bar(stage));
+          if (kb == k_blocks - 1) umma_commit_2sm(tfull_bar(acc));
+          if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue (both CTAs): this CTA's 128 rows of the 256-row tile =====
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    auto prefetch_residual = [&](int tile) {
+      if (EPI != EPI_F32_RESIDUAL || tile >= total_tiles) return;
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int row = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32 + lane;
+      if (row >= M) return;
+      const int col0 = n_blk * GEMM_BN + half * (GEMM_BN / 2);
+      const float* r = reinterpret_cast<const float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+#pragma unroll
+      for (int c = 0; c < GEMM_BN / 2; c += 32)
+        if (col0 + c < p.N) prefetch_l2(r + c);
+    };
+    prefetch_residual(pair);
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      prefetch_residual(tile + n_pairs);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+      for (int c = 0; c < GEMM_BN / 2; c += 32) {
+        const int col0 = n_blk * GEMM_BN + half * (GEMM_BN / 2) + c;
+        if (col0 >= p.N) break;
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(acc * GEMM_BN + half * (GEMM_BN / 2) + c);
+        tmem_ld32(taddr, v);
+        tmem_ld_wait();
+        if (row_ok) epilogue_chunk<EPI>(p, v, row, col0);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                       // nobody may still be reading the peer's smem / TMEM
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+}  // namespace leaf

@@ -173,6 +173,58 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
+// fused epilogue of one 32-column chunk of one accumulator row (v = raw fp32 bits from TMEM)
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, int row, int col0) {
+            float f[32];
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+  #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.N) {
+                  const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
+                  f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                }
+              }
+            }
+            if (EPI == EPI_BF16_ACT) {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act);
+            }
+            if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
+              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+  #pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (col0 + j < p.N) {
+                  uint4 pk;
+                  __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                  __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                  __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                  __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&t0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&t1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&t2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&t3);
+                  *reinterpret_cast<uint4*>(out + j) = pk;
+                }
+              }
+            } else {
+              float* out = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+  #pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.N) {
+                  float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                  if (EPI == EPI_F32_RESIDUAL) {
+                    const float4 r = *reinterpret_cast<const float4*>(out + j);
+                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                  }
+                  *reinterpret_cast<float4*>(out + j) = o;
+                }
+              }
+            }
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel
 // ---------------------------------------------------------------------------------------------
@@ -308,55 +360,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
                                static_cast<uint32_t>(acc * GEMM_BN + half * (GEMM_BN / 2) + c);
         tmem_ld32(taddr, v);
         tmem_ld_wait();
-        if (row_ok) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.N) {
-                const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            }
-          }
-          if (EPI == EPI_BF16_ACT) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act);
-          }
-          if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
-            __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.N) {
-                uint4 pk;
-                __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                *reinterpret_cast<uint4*>(out + j) = pk;
-              }
-            }
-          } else {
-            float* out = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.N) {
-                float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                if (EPI == EPI_F32_RESIDUAL) {
-                  const float4 r = *reinterpret_cast<const float4*>(out + j);
-                  o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                }
-                *reinterpret_cast<float4*>(out + j) = o;
-              }
-            }
-          }
-        }
+        if (row_ok) epilogue_chunk<EPI>(p, v, row, col0);
       }
       tc_fence_before();
       __syncwarp();
