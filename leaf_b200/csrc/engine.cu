@@ -56,7 +56,6 @@ struct leaf_engine {
   leaf_cfg_t cfg;
   int device = 0;
   int sm_count = 148;
-  bool force_1cta = false;           // LEAF_GEMM_1CTA=1: A/B switch to the single-CTA GEMM (bring-up / profiling)
   encode_tiled_fn encode_tiled = nullptr;
   // K1 tables
   bool bpe_loaded = false;
@@ -122,51 +121,37 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   if (M <= 0 || N <= 0 || K <= 0) return fail(LEAF_ERR_INVALID, "GEMM shape %dx%dx%d", M, N, K);
   if (N % 8 != 0) return fail(LEAF_ERR_INVALID, "GEMM N (%d) must be a multiple of 8", N);
   CUtensorMap ta, tb;
-  const bool pair_mode = !e->force_1cta;
   const int a_box = a_rows < 128 ? static_cast<int>(a_rows) : 128;
-  const int b_full = pair_mode ? 128 : GEMM_BN;
-  const int b_box = N < b_full ? N : b_full;
+  const int b_box = N < 128 ? N : 128;
   int rc = make_tmap(e, A, a_rows, K, a_box, &ta);
   if (rc) return rc;
   rc = make_tmap(e, Bt, N, K, b_box, &tb);
   if (rc) return rc;
   GemmParams p;
-  p.tx_bytes = static_cast<uint32_t>(a_box + b_box) * GEMM_BK * 2 * (pair_mode ? 2 : 1);
+  p.tx_bytes = static_cast<uint32_t>(a_box + b_box) * GEMM_BK * 2 * 2;       // both CTAs of the pair
   p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act;
-  const int bm = pair_mode ? GEMM2_BM : GEMM_BM;
-  const int m_tiles = (M + bm - 1) / bm, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
-  long tiles = static_cast<long>(m_tiles) * n_tiles;
+  const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
+  const long tiles = static_cast<long>(m_tiles) * n_tiles;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (e->timing) { e0 = get_event(e); e1 = get_event(e); cudaEventRecord(e0, st); }
-  if (pair_mode) {
-    const int pairs_max = e->sm_count / 2;
-    const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    switch (epi) {
-      case EPI_BF16: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_BF16>, ta, tb, p)); break;
-      case EPI_BF16_ACT: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_BF16_ACT>, ta, tb, p)); break;
-      case EPI_F32_RESIDUAL: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, ta, tb, p)); break;
-      case EPI_F32: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32>, ta, tb, p)); break;
-      default: return fail(LEAF_ERR_INVALID, "unknown epilogue %d", epi);
-    }
-  } else {
-    int grid = static_cast<int>(tiles < e->sm_count ? tiles : e->sm_count);
-    switch (epi) {
-      case EPI_BF16: gemm_bf16_tn_kernel<EPI_BF16><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p); break;
-      case EPI_BF16_ACT: gemm_bf16_tn_kernel<EPI_BF16_ACT><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p); break;
-      case EPI_F32_RESIDUAL: gemm_bf16_tn_kernel<EPI_F32_RESIDUAL><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p); break;
-      case EPI_F32: gemm_bf16_tn_kernel<EPI_F32><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p); break;
-      default: return fail(LEAF_ERR_INVALID, "unknown epilogue %d", epi);
-    }
+  const int pairs_max = e->sm_count / 2;
+  const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  switch (epi) {
+    case EPI_BF16: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_BF16>, ta, tb, p)); break;
+    case EPI_BF16_ACT: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_BF16_ACT>, ta, tb, p)); break;
+    case EPI_F32_RESIDUAL: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, ta, tb, p)); break;
+    case EPI_F32: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32>, ta, tb, p)); break;
+    default: return fail(LEAF_ERR_INVALID, "unknown epilogue %d", epi);
   }
   if (e->timing) { cudaEventRecord(e1, st); e->gemm_events.emplace_back(e0, e1); }
   e->launches++;
@@ -199,16 +184,10 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
     return fail(LEAF_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
   }
   e->encode_tiled = reinterpret_cast<encode_tiled_fn>(fn);
-  CK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI_BF16_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(gemm_bf16_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_BF16_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
-  const char* one = getenv("LEAF_GEMM_1CTA");
-  e->force_1cta = one && one[0] == '1';
   *out = e;
   return LEAF_OK;
 }

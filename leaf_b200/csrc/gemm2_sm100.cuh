@@ -4,7 +4,7 @@
 // would pull ~26 TB/s out of L2, more than twice what the L2 delivers, and ncu showed the 1-CTA kernel stuck near
 // 1.0-1.1 PFLOP/s (profiles/r1, r2). In a pair each CTA stages its own 128 rows of A and only HALF of the B tile
 // (128 of the 256 weight rows); tcgen05.mma.cta_group::2 (M256 N256 K16) reads both halves, so a CTA moves 32 KB per
-// 4.2 MFLOP (131 FLOP/B) and the ring holds 6 stages instead of 4.
+// 4.2 MFLOP (131 FLOP/B); the ring holds 5 stages and 36 KB are left for the epilogue's staging buffers.
 //
 // Protocol (per stage s; "leader" = CTA rank 0 of the pair):
 //   producers (warp 0 of BOTH CTAs) wait on their local empty[s], then TMA their A and B boxes into local smem with
@@ -20,11 +20,11 @@
 namespace leaf {
 
 constexpr int GEMM2_BM = 256;                 // per pair (128 per CTA)
-constexpr int GEMM2_STAGES = 6;
+constexpr int GEMM2_STAGES = 5;
 constexpr uint32_t GEMM2_A_BYTES = 128 * GEMM_BK * 2;
 constexpr uint32_t GEMM2_B_BYTES = 128 * GEMM_BK * 2;
 constexpr uint32_t GEMM2_STAGE_BYTES = GEMM2_A_BYTES + GEMM2_B_BYTES;
-constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 8 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA rank 0 of a pair
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -71,7 +71,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                      const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + GEMM2_STAGES * GEMM2_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + GEMM2_STAGES * GEMM2_STAGE_BYTES + 8 * EPI_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM2_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM2_STAGES + s); };
@@ -79,7 +79,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const uint32_t tmem_slot = bar_base + 8u * (2 * GEMM2_STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + GEMM2_STAGES * GEMM2_STAGE_BYTES + 8u * (2 * GEMM2_STAGES + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + GEMM2_STAGES * GEMM2_STAGE_BYTES + 8 * EPI_STAGE_BYTES +
+                                           8u * (2 * GEMM2_STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -166,6 +167,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     // ===== epilogue (both CTAs): this CTA's 128 rows of the 256-row tile =====
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
+    uint8_t* stage_buf = smem_gen + GEMM2_STAGES * GEMM2_STAGE_BYTES + (warp - 4) * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
     auto prefetch_residual = [&](int tile) {
@@ -185,8 +187,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       prefetch_residual(tile + n_pairs);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32 + lane;
-      const bool row_ok = row < M;
+      const int row0 = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32;
 #pragma unroll 1
       for (int c = 0; c < GEMM_BN / 2; c += 32) {
         const int col0 = n_blk * GEMM_BN + half * (GEMM_BN / 2) + c;
@@ -196,7 +197,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                                static_cast<uint32_t>(acc * GEMM_BN + half * (GEMM_BN / 2) + c);
         tmem_ld32(taddr, v);
         tmem_ld_wait();
-        if (row_ok) epilogue_chunk<EPI>(p, v, row, col0);
+        if (row0 < M) epilogue_chunk<EPI>(p, v, stage_buf, lane, row0, col0, M);      // warp-uniform
       }
       tc_fence_before();
       __syncwarp();

@@ -7,14 +7,15 @@
 // /root/reference/src/open_clip/model.py:282 text_projection). nn.Linear weights are [out,in] row-major,
 // i.e. already the K-major "B" operand, so no transpose is ever made.
 //
-// Structure (one persistent CTA per SM, 384 threads):
-//   warp 0      TMA producer   : cp.async.bulk.tensor 128B-swizzled A (128x64) and B (256x64) tiles into a
-//                                4-stage shared-memory ring, completion on mbarriers
-//   warp 1      MMA issuer     : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M128 N256 K16),
-//                                accumulators in TMEM, double buffered (2 x 256 columns)
+// This header holds the PTX wrappers, descriptors and the fused epilogue; the kernel itself (CTA-pair,
+// cta_group::2) is gemm2_sm100.cuh. Roles per CTA (384 threads):
+//   warp 0      TMA producer   : cp.async.bulk.tensor, 128B-swizzled 128x64 boxes of A and B into a shared-memory
+//                                ring, completion on mbarriers
+//   warp 1      MMA issuer     : one thread (leader CTA) issues tcgen05.mma.kind::f16, accumulators in TMEM,
+//                                double buffered (2 x 256 columns)
 //   warp 2      TMEM allocator
 //   warps 4-11  epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> fused bias / GELU / residual
-//                                -> global store; overlaps the next tile's MMAs through the TMEM double buffer
+//                                -> coalesced global store; overlaps the next tile's MMAs (TMEM double buffer)
 // M may be a device-side value (packed token rows are only known on the device).
 #pragma once
 #include <cuda.h>
@@ -24,16 +25,10 @@
 
 namespace leaf {
 
-constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
-constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_UMMA_K = 16;
 constexpr int GEMM_THREADS = 384;
-constexpr uint32_t GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;
-constexpr uint32_t GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;
-constexpr uint32_t GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
-constexpr uint32_t GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 enum { EPI_BF16 = 0, EPI_BF16_ACT = 1, EPI_F32_RESIDUAL = 2, EPI_F32 = 3 };
 enum { ACT_GELU_ERF = 0, ACT_QUICK_GELU = 1 };
@@ -173,208 +168,79 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 
-// fused epilogue of one 32-column chunk of one accumulator row (v = raw fp32 bits from TMEM)
+// Fused epilogue of one 32-row x 32-column chunk of the accumulator. Each lane arrives with one ROW of the chunk
+// (v = raw fp32 bits from TMEM, tcgen05.ld 32x32b); storing that directly would touch 32 different 128-byte lines per
+// instruction (ncu: the LSU wavefronts, not the tensor pipe, paced the K=1024 GEMMs). The chunk is therefore bounced
+// through a padded per-warp staging buffer and written out with full-line coalescing: 4 rows x 128 B (fp32) or
+// 8 rows x 64 B (bf16) per instruction. The fp32 residual is read with the same coalesced mapping.
+constexpr int EPI_STAGE_BYTES = 32 * 144;        // per warp: 32 rows, 128 B of data + 16 B pad (bank-conflict-free)
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, int row, int col0) {
-            float f[32];
-  #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias) {
-  #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (col0 + j < p.N) {
-                  const float4 b = *reinterpret_cast<const float4*>(p.bias + col0 + j);
-                  f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-                }
-              }
-            }
-            if (EPI == EPI_BF16_ACT) {
-  #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act);
-            }
-            if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
-              __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-  #pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                if (col0 + j < p.N) {
-                  uint4 pk;
-                  __nv_bfloat162 t0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                  __nv_bfloat162 t1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                  __nv_bfloat162 t2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                  __nv_bfloat162 t3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                  pk.x = *reinterpret_cast<uint32_t*>(&t0);
-                  pk.y = *reinterpret_cast<uint32_t*>(&t1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&t2);
-                  pk.w = *reinterpret_cast<uint32_t*>(&t3);
-                  *reinterpret_cast<uint4*>(out + j) = pk;
-                }
-              }
-            } else {
-              float* out = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-  #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                if (col0 + j < p.N) {
-                  float4 o = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                  if (EPI == EPI_F32_RESIDUAL) {
-                    const float4 r = *reinterpret_cast<const float4*>(out + j);
-                    o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
-                  }
-                  *reinterpret_cast<float4*>(out + j) = o;
-                }
-              }
-            }
-}
-
-// ---------------------------------------------------------------------------------------------
-// kernel
-// ---------------------------------------------------------------------------------------------
-template <int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                    const GemmParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // SWIZZLE_128B needs 1024 B alignment
-  const uint32_t bar_base = smem_base + GEMM_STAGES * GEMM_STAGE_BYTES;
-  // barrier layout (8 B each): full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base word
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * GEMM_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * GEMM_STAGES + 4);
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + GEMM_STAGES * GEMM_STAGE_BYTES +
-                                                                         8u * (2 * GEMM_STAGES + 4));
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int M = p.m_dev ? min(*p.m_dev, p.M) : p.M;
-  const int m_tiles = (M + GEMM_BM - 1) / GEMM_BM;
-  const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
-  const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int total_tiles = m_tiles * n_tiles;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_a);
-    tma_prefetch_desc(&tmap_b);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < GEMM_STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 8);       // one arrival per epilogue warp
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_gen;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
-          const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
-          const uint32_t sb = sa + GEMM_A_BYTES;
-          mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
-          tma_load_2d(sa, &tmap_a, full_bar(stage), kb * GEMM_BK, m_blk * GEMM_BM);
-          tma_load_2d(sb, &tmap_b, full_bar(stage), kb * GEMM_BK, n_blk * GEMM_BN);
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer (a single thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM_BM, GEMM_BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);      // epilogue has drained this accumulator
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * GEMM_BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * GEMM_STAGE_BYTES;
-          const uint32_t sb = sa + GEMM_A_BYTES;
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sb);
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, uint8_t* stage, int lane,
+                                               int row0, int col0, int M) {
+  float f[32];
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k) {
-            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(empty_bar(stage));                 // frees the smem stage when these MMAs retire
-          if (kb == k_blocks - 1) umma_commit(tfull_bar(acc));
-          if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
-        }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else if (warp >= 4) {
-    // ===== epilogue: 8 warps, quadrant = warp % 4 (TMEM lane window), column half = (warp - 4) / 4 =====
-    const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    // residual epilogue: the fp32 tile it will read-modify-write is pulled into L2 one tile ahead, while the MMAs of
-    // that tile are still running (the out-proj GEMM sits at the HBM/tensor ridge, profiles/r1)
-    auto prefetch_residual = [&](int tile) {
-      if (EPI != EPI_F32_RESIDUAL || tile >= total_tiles) return;
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int row = m_blk * GEMM_BM + quad * 32 + lane;
-      if (row >= M) return;
-      const int col0 = n_blk * GEMM_BN + half * (GEMM_BN / 2);
-      const float* r = reinterpret_cast<const float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias) {
 #pragma unroll
-      for (int c = 0; c < GEMM_BN / 2; c += 32)
-        if (col0 + c < p.N) prefetch_l2(r + c);
-    };
-    prefetch_residual(blockIdx.x);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      prefetch_residual(tile + gridDim.x);
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-      const int row = m_blk * GEMM_BM + quad * 32 + lane;
-      const bool row_ok = row < M;
-#pragma unroll 1
-      for (int c = 0; c < GEMM_BN / 2; c += 32) {
-        const int col0 = n_blk * GEMM_BN + half * (GEMM_BN / 2) + c;
-        if (col0 >= p.N) break;                          // warp-uniform
-        uint32_t v[32];
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>(acc * GEMM_BN + half * (GEMM_BN / 2) + c);
-        tmem_ld32(taddr, v);
-        tmem_ld_wait();
-        if (row_ok) epilogue_chunk<EPI>(p, v, row, col0);
+    for (int j = 0; j < 32; j += 4) {
+      if (col0 + j < p.N) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+        f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+  if (EPI == EPI_BF16_ACT) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act);
   }
+  if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
+    // rows of 64 B at a stride of 80 B: 16-byte writes of 8 consecutive lanes hit 8 distinct bank groups
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint4 pk;
+      __nv_bfloat162 t0 = __floats2bfloat162_rn(f[8 * q], f[8 * q + 1]);
+      __nv_bfloat162 t1 = __floats2bfloat162_rn(f[8 * q + 2], f[8 * q + 3]);
+      __nv_bfloat162 t2 = __floats2bfloat162_rn(f[8 * q + 4], f[8 * q + 5]);
+      __nv_bfloat162 t3 = __floats2bfloat162_rn(f[8 * q + 6], f[8 * q + 7]);
+      pk.x = *reinterpret_cast<uint32_t*>(&t0);
+      pk.y = *reinterpret_cast<uint32_t*>(&t1);
+      pk.z = *reinterpret_cast<uint32_t*>(&t2);
+      pk.w = *reinterpret_cast<uint32_t*>(&t3);
+      *reinterpret_cast<uint4*>(stage + lane * 80 + q * 16) = pk;
+    }
+    __syncwarp();
+    const int c = lane & 3;
+    const bool col_ok = col0 + c * 8 < p.N;
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2);
+      const uint4 pk = *reinterpret_cast<const uint4*>(stage + r * 80 + c * 16);
+      if (col_ok && row0 + r < M)
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row0 + r) * p.ldc + col0 + c * 8) = pk;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      *reinterpret_cast<float4*>(stage + lane * 144 + q * 16) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+    __syncwarp();
+    const int c = lane & 7;
+    const bool col_ok = col0 + c * 4 < p.N;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3);
+      float4 o = *reinterpret_cast<const float4*>(stage + r * 144 + c * 16);
+      if (col_ok && row0 + r < M) {
+        float* out = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row0 + r) * p.ldc + col0 + c * 4;
+        if (EPI == EPI_F32_RESIDUAL) {
+          const float4 x = *reinterpret_cast<const float4*>(out);
+          o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+        }
+        *reinterpret_cast<float4*>(out) = o;
+      }
+    }
+  }
+  __syncwarp();                                   // the staging buffer is reused by the next chunk
 }
 
 }  // namespace leaf
