@@ -4,7 +4,7 @@
 // would pull ~26 TB/s out of L2, more than twice what the L2 delivers, and ncu showed the 1-CTA kernel stuck near
 // 1.0-1.1 PFLOP/s (profiles/r1, r2). In a pair each CTA stages its own 128 rows of A and only HALF of the B tile
 // (128 of the 256 weight rows); tcgen05.mma.cta_group::2 (M256 N256 K16) reads both halves, so a CTA moves 32 KB per
-// 4.2 MFLOP (131 FLOP/B); the ring holds 5 stages and 36 KB are left for the epilogue's staging buffers.
+// 4.2 MFLOP (131 FLOP/B); the ring holds 5 stages and 40 KB are left for the 16 epilogue warps' staging buffers.
 //
 // Protocol (per stage s; "leader" = CTA rank 0 of the pair):
 //   producers (warp 0 of BOTH CTAs) wait on their local empty[s], then TMA their A and B boxes into local smem with
@@ -13,7 +13,7 @@
 //   the leader's MMA thread waits full[s], issues 4 MMAs, then tcgen05.commit...multicast::cluster arrives on empty[s]
 //     of both CTAs (and on tmem_full[acc] of both after the last k-block);
 //   epilogue warps of both CTAs drain their own 128 TMEM lanes and arrive (remotely for the peer) on the leader's
-//     tmem_empty[acc] (count 16).
+//     tmem_empty[acc] (count 2 x 16 warps).
 #pragma once
 #include "gemm_sm100.cuh"
 
@@ -24,7 +24,7 @@ constexpr int GEMM2_STAGES = 5;
 constexpr uint32_t GEMM2_A_BYTES = 128 * GEMM_BK * 2;
 constexpr uint32_t GEMM2_B_BYTES = 128 * GEMM_BK * 2;
 constexpr uint32_t GEMM2_STAGE_BYTES = GEMM2_A_BYTES + GEMM2_B_BYTES;
-constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + 8 * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;   // shared::cluster address of the same offset in CTA rank 0 of a pair
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -71,7 +71,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                      const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + GEMM2_STAGES * GEMM2_STAGE_BYTES + 8 * EPI_STAGE_BYTES;
+  const uint32_t bar_base = smem_base + GEMM2_STAGES * GEMM2_STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM2_STAGES + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * GEMM2_STAGES + s); };
@@ -79,7 +79,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const uint32_t tmem_slot = bar_base + 8u * (2 * GEMM2_STAGES + 4);
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + GEMM2_STAGES * GEMM2_STAGE_BYTES + 8 * EPI_STAGE_BYTES +
+      reinterpret_cast<volatile uint32_t*>(smem_gen + GEMM2_STAGES * GEMM2_STAGE_BYTES + EPI_WARPS * EPI_STAGE_BYTES +
                                            8u * (2 * GEMM2_STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
@@ -104,7 +104,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);          // multicast commit
-      mbar_init(tempty_bar(s), 16);        // 8 epilogue warps of each CTA (leader's copy is the one waited on)
+      mbar_init(tempty_bar(s), 2 * EPI_WARPS);   // every epilogue warp of both CTAs (leader's copy is the one waited on)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -166,7 +166,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   } else if (warp >= 4) {
     // ===== epilogue (both CTAs): this CTA's 128 rows of the 256-row tile =====
     const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int part = (warp - 4) >> 2;          // which 64 accumulator columns
     uint8_t* stage_buf = smem_gen + GEMM2_STAGES * GEMM2_STAGE_BYTES + (warp - 4) * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -175,10 +175,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
       const int row = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32 + lane;
       if (row >= M) return;
-      const int col0 = n_blk * GEMM_BN + half * (GEMM_BN / 2);
+      const int col0 = n_blk * GEMM_BN + part * 64;
       const float* r = reinterpret_cast<const float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
 #pragma unroll
-      for (int c = 0; c < GEMM_BN / 2; c += 32)
+      for (int c = 0; c < 64; c += 32)
         if (col0 + c < p.N) prefetch_l2(r + c);
     };
     prefetch_residual(pair);
@@ -189,15 +189,17 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       tc_fence_after();
       const int row0 = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32;
 #pragma unroll 1
-      for (int c = 0; c < GEMM_BN / 2; c += 32) {
-        const int col0 = n_blk * GEMM_BN + half * (GEMM_BN / 2) + c;
+      for (int c = 0; c < 64; c += 32) {
+        const int col0 = n_blk * GEMM_BN + part * 64 + c;
         if (col0 >= p.N) break;
+        ResidualRegs res;
+        if (row0 < M) epilogue_load_residual<EPI>(p, res, lane, row0, col0, M);
         uint32_t v[32];
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>(acc * GEMM_BN + half * (GEMM_BN / 2) + c);
+                               static_cast<uint32_t>(acc * GEMM_BN + part * 64 + c);
         tmem_ld32(taddr, v);
         tmem_ld_wait();
-        if (row0 < M) epilogue_chunk<EPI>(p, v, stage_buf, lane, row0, col0, M);      // warp-uniform
+        if (row0 < M) epilogue_chunk<EPI>(p, v, res, stage_buf, lane, row0, col0, M);      // warp-uniform
       }
       tc_fence_before();
       __syncwarp();

@@ -8,13 +8,13 @@
 // i.e. already the K-major "B" operand, so no transpose is ever made.
 //
 // This header holds the PTX wrappers, descriptors and the fused epilogue; the kernel itself (CTA-pair,
-// cta_group::2) is gemm2_sm100.cuh. Roles per CTA (384 threads):
+// cta_group::2) is gemm2_sm100.cuh. Roles per CTA (640 threads):
 //   warp 0      TMA producer   : cp.async.bulk.tensor, 128B-swizzled 128x64 boxes of A and B into a shared-memory
 //                                ring, completion on mbarriers
 //   warp 1      MMA issuer     : one thread (leader CTA) issues tcgen05.mma.kind::f16, accumulators in TMEM,
 //                                double buffered (2 x 256 columns)
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> fused bias / GELU / residual
+//   warps 4-19  epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> fused bias / GELU / residual
 //                                -> coalesced global store; overlaps the next tile's MMAs (TMEM double buffer)
 // M may be a device-side value (packed token rows are only known on the device).
 #pragma once
@@ -28,7 +28,6 @@ namespace leaf {
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_UMMA_K = 16;
-constexpr int GEMM_THREADS = 384;
 
 enum { EPI_BF16 = 0, EPI_BF16_ACT = 1, EPI_F32_RESIDUAL = 2, EPI_F32 = 3 };
 enum { ACT_GELU_ERF = 0, ACT_QUICK_GELU = 1 };
@@ -145,24 +144,23 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// nn.GELU (erf form): 0.5 x (1 + erf(x / sqrt 2)). erfc(z) = poly(t) exp(-z^2), t = 1/(1 + p z) (Abramowitz-Stegun
-// 7.1.26, |error| <= 1.5e-7 on erf), evaluated on |x| so that the negative tail has no cancellation. ~14 FP32 ops
-// + 2 MUFU per element: libdevice's erff costs ~39 instructions and made the fc1 epilogue the bottleneck (profiles/).
+// nn.GELU (erf form): x Phi(x) = max(x, 0) - g,  g = 0.5 |x| erfc(|x| / sqrt 2) >= 0.
+// erfc(z) = poly(t) exp(-z^2), t = 1 / (1 + p z) (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 on erf); evaluated on |x|
+// so the negative tail has no cancellation. The 0.5 and the 1/sqrt 2 are folded into the constants:
+// 12 FP32 ops + 2 MUFU per element (libdevice's erff costs ~39 instructions and paced the fc1 GEMM, profiles/r1).
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = fast_rcp(fmaf(0.3275911f, z, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(t, poly, 1.421413741f);
-  poly = fmaf(t, poly, -0.284496736f);
-  poly = fmaf(t, poly, 0.254829592f);
-  poly *= t;
-  const float e = fast_ex2(x * x * -0.72134752044448170368f);            // exp(-x^2 / 2)
-  const float h = 0.5f * x * poly * e;                                   // 0.5 x erfc(|x| / sqrt 2)
-  return x >= 0.f ? x - h : h;
+  const float a = fabsf(x);
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752440f, a, 1.0f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(t, poly, 0.5f * 1.421413741f);
+  poly = fmaf(t, poly, 0.5f * -0.284496736f);
+  poly = fmaf(t, poly, 0.5f * 0.254829592f);
+  const float e = fast_ex2(a * -0.72134752044448170368f * a);            // exp(-x^2 / 2)
+  const float g = (poly * t) * (a * e);
+  return fmaxf(x, 0.f) - g;
 }
-__device__ __forceinline__ float act_apply(float x, int act) {
-  if (act == ACT_QUICK_GELU) return x * fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));   // x sigmoid(1.702 x)
-  return gelu_erf(x);
+__device__ __forceinline__ float quick_gelu(float x) {                   // x sigmoid(1.702 x), transformer.py:33-36
+  return x * fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));
 }
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
@@ -170,14 +168,36 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 
 // Fused epilogue of one 32-row x 32-column chunk of the accumulator. Each lane arrives with one ROW of the chunk
 // (v = raw fp32 bits from TMEM, tcgen05.ld 32x32b); storing that directly would touch 32 different 128-byte lines per
-// instruction (ncu: the LSU wavefronts, not the tensor pipe, paced the K=1024 GEMMs). The chunk is therefore bounced
-// through a padded per-warp staging buffer and written out with full-line coalescing: 4 rows x 128 B (fp32) or
-// 8 rows x 64 B (bf16) per instruction. The fp32 residual is read with the same coalesced mapping.
-constexpr int EPI_STAGE_BYTES = 32 * 144;        // per warp: 32 rows, 128 B of data + 16 B pad (bank-conflict-free)
+// instruction (ncu r3: LSU wavefronts, not the tensor pipe, paced the K=1024 GEMMs). The chunk is bounced through a
+// padded per-warp staging buffer (rows of 64 B at a stride of 80 B: the 16-byte accesses of 8 consecutive lanes hit 8
+// distinct bank groups) and written with 8 rows x 64 B per instruction. bf16 outputs take one pass (32 columns),
+// fp32 outputs two passes of 16 columns. The fp32 residual is loaded with the same mapping BEFORE the accumulator is
+// read from TMEM, so its latency hides behind the TMEM load and the bias/activation math.
+constexpr int EPI_WARPS = 16;                    // 4 per TMEM lane quadrant, 64 accumulator columns each
+constexpr int EPI_STAGE_BYTES = 32 * 80;         // per warp
+constexpr int GEMM_THREADS = 128 + 32 * EPI_WARPS;
+
+struct ResidualRegs { float4 x[8]; };
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, uint8_t* stage, int lane,
-                                               int row0, int col0, int M) {
+__device__ __forceinline__ void epilogue_load_residual(const GemmParams& p, ResidualRegs& r, int lane, int row0, int col0, int M) {
+  if (EPI != EPI_F32_RESIDUAL) return;
+  const int c = lane & 3;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int row = row0 + it * 8 + (lane >> 2);
+      const int col = col0 + h * 16 + c * 4;
+      if (row < M && col < p.N)
+        r.x[h * 4 + it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.C) + static_cast<size_t>(row) * p.ldc + col);
+    }
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t* v, const ResidualRegs& res, uint8_t* stage,
+                                               int lane, int row0, int col0, int M) {
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -191,11 +211,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
   }
   if (EPI == EPI_BF16_ACT) {
+    if (p.act == ACT_QUICK_GELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = act_apply(f[j], p.act);
+      for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    }
   }
+  const int c = lane & 3;
   if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
-    // rows of 64 B at a stride of 80 B: 16-byte writes of 8 consecutive lanes hit 8 distinct bank groups
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 pk;
@@ -210,7 +235,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       *reinterpret_cast<uint4*>(stage + lane * 80 + q * 16) = pk;
     }
     __syncwarp();
-    const int c = lane & 3;
     const bool col_ok = col0 + c * 8 < p.N;
 #pragma unroll
     for (int it = 0; it < 4; ++it) {
@@ -219,28 +243,31 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       if (col_ok && row0 + r < M)
         *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row0 + r) * p.ldc + col0 + c * 8) = pk;
     }
+    __syncwarp();                                 // the staging buffer is reused by the next chunk
   } else {
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      *reinterpret_cast<float4*>(stage + lane * 144 + q * 16) = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-    __syncwarp();
-    const int c = lane & 7;
-    const bool col_ok = col0 + c * 4 < p.N;
+    for (int h = 0; h < 2; ++h) {
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + (lane >> 3);
-      float4 o = *reinterpret_cast<const float4*>(stage + r * 144 + c * 16);
-      if (col_ok && row0 + r < M) {
-        float* out = reinterpret_cast<float*>(p.C) + static_cast<size_t>(row0 + r) * p.ldc + col0 + c * 4;
-        if (EPI == EPI_F32_RESIDUAL) {
-          const float4 x = *reinterpret_cast<const float4*>(out);
-          o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(stage + lane * 80 + q * 16) =
+            make_float4(f[16 * h + 4 * q], f[16 * h + 4 * q + 1], f[16 * h + 4 * q + 2], f[16 * h + 4 * q + 3]);
+      __syncwarp();
+      const int col = col0 + h * 16 + c * 4;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = it * 8 + (lane >> 2);
+        float4 o = *reinterpret_cast<const float4*>(stage + r * 80 + c * 16);
+        if (col < p.N && row0 + r < M) {
+          if (EPI == EPI_F32_RESIDUAL) {
+            const float4 x = res.x[h * 4 + it];
+            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+          }
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + static_cast<size_t>(row0 + r) * p.ldc + col) = o;
         }
-        *reinterpret_cast<float4*>(out) = o;
       }
+      __syncwarp();
     }
   }
-  __syncwarp();                                   // the staging buffer is reused by the next chunk
 }
 
 }  // namespace leaf
