@@ -267,8 +267,14 @@ def run_ours(a):
     peak_tf, peak_gbs, peak_src = peaks()
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     step_ms = dev_ms / a.steps
-    roofline = dict(bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=None,
-                    kernel="gemm_bf16_tn_kernel (tcgen05)", peak_source=peak_src, gemm_launches_per_step=gemm_launches,
+    traffic = None                                  # DRAM bytes per GEMM launch from the committed ncu --set full capture
+    tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("workload") == workload_name(a):
+            traffic = tj["dram_bytes_per_launch"]
+    roofline = dict(bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=traffic,
+                    kernel="gemm2_bf16_tn_kernel (tcgen05.mma.cta_group::2, all four Linear layers + projection)", peak_source=peak_src, gemm_launches_per_step=gemm_launches,
                     gemm_ms_per_step=gemm_ms, gemm_share_of_step=gemm_ms / step_ms if step_ms else None,
                     algorithmic_tflop_per_step=alg_flops / 1e12, executed_gemm_tflop_per_step=gemm_flops / 1e12,
                     credited_gemm_tflops=gemm_flops_credit / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
