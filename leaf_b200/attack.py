@@ -21,6 +21,7 @@ import string
 import numpy as np
 import torch
 
+from . import dist as D
 from ._native import LeafError
 from .engine import LeafEngine, OBJECTIVES
 
@@ -43,8 +44,13 @@ def generate_sentence(S: str, z: int, c: int) -> str:
     return S[:i] + chr(c) + S[i:]
 
 
+def _to_dev(a: np.ndarray, dev) -> torch.Tensor:
+    t = torch.from_numpy(a)
+    return t.pin_memory().to(dev, non_blocking=True) if torch.device(dev).type == "cuda" else t
+
+
 def _engine_of(model) -> LeafEngine:
-    if isinstance(model, LeafEngine):
+    if isinstance(model, LeafEngine) or all(hasattr(model, a) for a in ("expand_tokenize", "encode_tokens", "score")):
         return model
     eng = getattr(model, "leaf_engine", None)
     if isinstance(eng, LeafEngine):
@@ -81,13 +87,21 @@ def _valid_mask(constrain, sentences, SS, B, n, device):
     The reference's filter (valid_sentence_batched, :110-143) needs NLTK corpora; here it is a host callable
     constrain(sentences, SS) -> bool[B][n] supplied by the caller (parity unpinned)."""
     valid = np.asarray(constrain(sentences, SS), dtype=np.uint8).reshape(B, n)
-    return torch.from_numpy(valid).pin_memory().to(device, non_blocking=True)
+    return _to_dev(valid, device)
 
 
 def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, objective="l2", n=10, k=1, V=V_DEFAULT,
-                     constrain=False, debug=False):
+                     constrain=False, debug=False, *, shard=None, group=None):
+    """utils_attacks.py:297-393. Extra keyword-only arguments (not in the reference):
+    shard = None         every process attacks the batch it was given (the reference's data-parallel meaning);
+    shard = "samples"    `sentences`/`anchor_features` are the GLOBAL batch, identical on every rank; rank r attacks its
+                         slice of samples, winners are all-gathered, every rank returns the global result;
+    shard = "candidates" global batch on every rank; rank r scores its slice of the n candidates of every sample and
+                         the per-sample argmax is completed across ranks (leaf_b200/dist.py)."""
     if objective not in OBJECTIVES:
         raise ValueError(f"unknown objective {objective!r}")                  # reference: falls through with loss undefined
+    if shard not in (None, "samples", "candidates"):
+        raise ValueError(f"unknown shard mode {shard!r}")
     eng = _engine_of(model)
     if constrain is True:
         raise LeafError("constrain=True needs the reference's NLTK word list, which cannot be reproduced offline; pass "
@@ -100,53 +114,92 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
     Vt = np.asarray(V, dtype=np.int32)
     if Vt.min() < -1 or Vt.max() > 0x7F:
         raise LeafError("attack alphabet V must hold -1 or ASCII code points")
+    rank, G = D.world(group) if shard else (0, 1)
+    blo, bhi = D.shard_range(B, rank, G) if shard == "samples" else (0, B)      # samples this rank attacks
+    jlo, jhi = D.shard_range(n, rank, G) if shard == "candidates" else (0, n)   # candidates this rank scores
+    Bl, nl = bhi - blo, jhi - jlo
     anchor = anchor_features
     if objective in ("dissim", "sim"):
         anchor /= anchor.norm(dim=-1, keepdim=True)                           # in place, as :304-308
-    anchor = anchor.to(device=dev, dtype=torch.float32).contiguous()
+    anchor = anchor.to(device=dev, dtype=torch.float32)[blo:bhi].contiguous()
     normalize = objective in ("sim", "dissim")
-    eng.reserve(B * n + B)
     best_feat = None
+    if Bl > 0 and nl > 0:
+        eng.reserve(Bl * nl + Bl)
     for _ in range(k):
         lens = [len(S) for S in sentences]
-        # --- host: the reference's draws, in the reference's order (pre-drawn: SURVEY.md appendix E) ---
+        # --- host: the reference's draws for the WHOLE batch, in the reference's order (pre-drawn: SURVEY.md app. E) ---
         positions = np.stack([np.random.choice(range(2 * L + 1), size=n, replace=n > 2 * L + 1) for L in lens])  # :317
         us = np.stack([np.random.choice(range(len(V)), size=n, replace=(n > len(V))) for _ in sentences])       # :236
         chars2 = Vt[us]
-        caps_d, off_d = eng.upload_captions(sentences)
-        host = np.concatenate([positions.astype(np.int32).ravel(), np.full(B * n, 32, dtype=np.int32), chars2.ravel()])
-        host_d = torch.from_numpy(host).pin_memory().to(dev, non_blocking=True)
-        pos_d, chr1_d, chr2_d = host_d[:B * n], host_d[B * n:2 * B * n], host_d[2 * B * n:]
-        # --- phase 1: choose the position (a space at each drawn z), :316-353 ---
-        valid1 = None
-        if valid_fn is not None:
-            SS = [[generate_sentence(S, int(z), 32) for z in positions[i]] for i, S in enumerate(sentences)]
-            valid1 = _valid_mask(valid_fn, sentences, SS, B, n, dev)
-        tok, ln, base = eng.expand_tokenize(caps_d, off_d, B, n, pos=pos_d, chr_=chr1_d, valid=valid1)
-        feats = eng.encode_tokens(tok, ln, normalize, base)          # rows [0, B*n) candidates, then the B captions
-        best1, _, loss1 = eng.score(feats, anchor, B, n, objective, want_loss=debug)
-        # --- phase 2: choose the character at the best position, :355-389 ---
-        valid2 = None
-        if valid_fn is not None:
-            b1 = best1.cpu().numpy()
-            zs = positions[np.arange(B), b1]
-            SS = [[generate_sentence(S, int(zs[i]), int(c)) for c in chars2[i]] for i, S in enumerate(sentences)]
-            valid2 = _valid_mask(valid_fn, sentences, SS, B, n, dev)
-        tok, ln, base = eng.expand_tokenize(caps_d, off_d, B, n, pos=pos_d, chr_=chr2_d, sel=best1, valid=valid2)
-        feats = eng.encode_tokens(tok, ln, normalize, base)
-        best2, best_feat, loss2 = eng.score(feats, anchor, B, n, objective, want_loss=debug)
-        # --- one small D2H per round: the 2B winner indices (+ tokenizer status) ---
-        picks = torch.stack([best1, best2]).cpu().numpy()
-        eng.check_status()
+        mine = sentences[blo:bhi]
+        pos_l = np.ascontiguousarray(positions[blo:bhi, jlo:jhi]).astype(np.int32)
+        chr2_l = np.ascontiguousarray(chars2[blo:bhi, jlo:jhi])
+        picks = np.zeros((2, B), dtype=np.int64)                              # global candidate index per phase
+        feat_l = torch.zeros((Bl, eng.embed_dim), dtype=torch.float32, device=dev)
+        ok2 = np.ones(B, dtype=bool)
+        if Bl > 0 and nl > 0:
+            caps_d, off_d = eng.upload_captions(mine)
+            host = np.concatenate([pos_l.ravel(), np.full(Bl * nl, 32, dtype=np.int32), chr2_l.ravel()])
+            host_d = _to_dev(host, dev)
+            pos_d, chr1_d, chr2_d = host_d[:Bl * nl], host_d[Bl * nl:2 * Bl * nl], host_d[2 * Bl * nl:]
+            # --- phase 1: choose the position (a space at each drawn z), :316-353 ---
+            valid1 = None
+            if valid_fn is not None:
+                SS = [[generate_sentence(S, int(z), 32) for z in pos_l[i]] for i, S in enumerate(mine)]
+                valid1 = _valid_mask(valid_fn, mine, SS, Bl, nl, dev)
+            tok, ln, base = eng.expand_tokenize(caps_d, off_d, Bl, nl, pos=pos_d, chr_=chr1_d, valid=valid1)
+            feats = eng.encode_tokens(tok, ln, normalize, base)      # rows [0, Bl*nl) candidates, then the Bl captions
+            best1, _, loss1 = eng.score(feats, anchor, Bl, nl, objective, want_loss=(debug or shard == "candidates"))
+        if shard == "candidates":
+            val1 = loss1.gather(1, best1.long().view(-1, 1)).squeeze(1)
+            _, g1 = D.cross_shard_argmax(val1, best1.long() + jlo, group)     # global index of the best position
+            zstar = torch.from_numpy(positions.astype(np.int32)).to(dev).gather(1, g1.view(-1, 1)).squeeze(1)
+            pos2_d = zstar.view(-1, 1).expand(Bl, nl).contiguous()            # same position for every candidate
+            sel = None
+        elif Bl > 0:
+            g1, pos2_d, sel = best1.long(), pos_d, best1
+        if Bl > 0 and nl > 0:
+            # --- phase 2: choose the character at the best position, :355-389 ---
+            valid2 = None
+            if valid_fn is not None:
+                zs_l = positions[np.arange(blo, bhi), g1.cpu().numpy()]
+                SS = [[generate_sentence(S, int(zs_l[i]), int(c)) for c in chr2_l[i]] for i, S in enumerate(mine)]
+                valid2 = _valid_mask(valid_fn, mine, SS, Bl, nl, dev)
+            tok, ln, base = eng.expand_tokenize(caps_d, off_d, Bl, nl, pos=pos2_d, chr_=chr2_d, sel=sel, valid=valid2)
+            feats = eng.encode_tokens(tok, ln, normalize, base)
+            best2, feat_l, loss2 = eng.score(feats, anchor, Bl, nl, objective, want_loss=(debug or shard == "candidates"))
+            g2 = best2.long()
+            okv = torch.ones(Bl, dtype=torch.bool, device=dev) if valid2 is None else \
+                valid2.view(Bl, nl).gather(1, g2.view(-1, 1)).squeeze(1).bool()
+        if shard == "candidates":
+            val2 = loss2.gather(1, g2.view(-1, 1)).squeeze(1)
+            _, gg2 = D.cross_shard_argmax(val2, g2 + jlo, group)
+            owner = torch.zeros(B, dtype=torch.long, device=dev)
+            for r in range(G):
+                lo, hi = D.shard_range(n, r, G)
+                owner[(gg2 >= lo) & (gg2 < hi)] = r
+            feat_l = D.broadcast_rows(feat_l, owner, group)                   # winner's features from the rank that has them
+            okv = D.broadcast_rows(okv.to(torch.float32), owner, group) > 0.5
+            g2 = gg2
+        # --- one small D2H per round: the winner indices (+ tokenizer status) ---
+        if Bl > 0 and nl > 0:
+            local = torch.stack([g1, g2, okv.long()]).cpu().numpy()
+            eng.check_status()
+        else:
+            local = np.zeros((3, 0), dtype=np.int64)
+        if shard == "samples" and G > 1:
+            sizes = [D.shard_range(B, r, G)[1] - D.shard_range(B, r, G)[0] for r in range(G)]
+            allp = D.all_gather_cat(torch.from_numpy(local.T.copy()).to(dev), sizes, group).cpu().numpy().T
+            best_feat = D.all_gather_cat(feat_l, sizes, group)
+        else:
+            allp, best_feat = local, feat_l
+        picks[0], picks[1], ok2 = allp[0], allp[1], allp[2].astype(bool)
         zs = positions[np.arange(B), picks[0]]
         cs = chars2[np.arange(B), picks[1]]
-        new = []
-        for i, S in enumerate(sentences):
-            ok = valid2 is None or bool(valid2[i, picks[1][i]].item())
-            new.append(generate_sentence(S, int(zs[i]), int(cs[i])) if ok else S)
+        sentences = [generate_sentence(S, int(zs[i]), int(cs[i])) if ok2[i] else S for i, S in enumerate(sentences)]
         if debug:
             print("LEAF round: best positions", zs.tolist(), "chars", cs.tolist())
-        sentences = new
     return best_feat, sentences
 
 

@@ -1,0 +1,102 @@
+"""Host logic of leaf_b200.attack_text_leaf on the CPU with the oracle-backed engine double (tests/oracle_engine.py):
+the reference's draw order and phase chaining against the golden attack runs, and the two sharding modes under a
+world_size-2 gloo group against the unsharded result."""
+import json
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from leaf_b200 import attack_text_leaf, synth
+from leaf_b200 import dist as D
+from tests.oracle_engine import OracleEngine
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _setup():
+    g = json.load(open(os.path.join(GOLDEN, "attack_golden.json")))
+    z = np.load(os.path.join(GOLDEN, "attack_golden.npz"))
+    cfg = synth.TOWERS[g["tower"]]
+    sd = synth.random_tower_state_dict(cfg, seed=g["seed"], exact_numpy=True)
+    return g, z, cfg, sd
+
+
+def test_attack_driver_reproduces_reference_runs():
+    g, z, cfg, sd = _setup()
+    eng = OracleEngine(sd, cfg.heads)
+    for ci, c in enumerate(g["cases"]):
+        np.random.seed(c["seed"])
+        feats, adv = attack_text_leaf(eng, None, c["captions"], torch.from_numpy(z[f"anchor_{ci}"]).clone(), "cpu",
+                                      objective=c["objective"], n=c["n"], k=c["k"])
+        assert adv == c["adv"], ci
+        assert np.abs(feats.numpy() - z[f"feats_{ci}"]).max() < 1e-4
+
+
+def test_constraint_mask_replaces_candidates_by_the_current_sentence():
+    g, z, cfg, sd = _setup()
+    eng = OracleEngine(sd, cfg.heads)
+    c = g["cases"][0]
+    np.random.seed(c["seed"])
+    nothing_valid = lambda sentences, SS: [[False] * len(SS[0]) for _ in sentences]
+    _, adv = attack_text_leaf(eng, None, c["captions"], torch.from_numpy(z["anchor_0"]).clone(), "cpu", n=c["n"], k=1,
+                              constrain=nothing_valid)
+    assert adv == c["captions"]                       # utils_attacks.py:325/:364: invalid -> the sentence itself
+
+
+def test_cross_shard_argmax_single_process():
+    v, i = torch.tensor([1.0, 2.0]), torch.tensor([3, 4])
+    assert D.cross_shard_argmax(v, i) == (v, i)
+    assert D.shard_range(10, 0, 3) == (0, 3) and D.shard_range(10, 2, 3) == (6, 10)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    g, z, cfg, sd = _setup()
+    res = {}
+    # first-index tie-break across shards: ties must resolve to the smallest GLOBAL index
+    val = torch.tensor([5.0, 1.0, 7.0]) if rank == 0 else torch.tensor([5.0, 2.0, 7.0])
+    idx = torch.tensor([4, 0, 9]) if rank == 0 else torch.tensor([2, 6, 11])
+    gv, gi = D.cross_shard_argmax(val, idx)
+    res["argmax"] = (gv.tolist(), gi.tolist())
+    for mode in ("samples", "candidates"):
+        for ci in (1, 3):                             # k=1 n=50 and k=2 n=20
+            c = g["cases"][ci]
+            eng = OracleEngine(sd, cfg.heads)
+            np.random.seed(c["seed"])
+            feats, adv = attack_text_leaf(eng, None, c["captions"], torch.from_numpy(z[f"anchor_{ci}"]).clone(), "cpu",
+                                          objective=c["objective"], n=c["n"], k=c["k"], shard=mode)
+            res[(mode, ci)] = (adv, float(np.abs(feats.numpy() - z[f"feats_{ci}"]).max()), eng.encoded_rows)
+    out[rank] = res
+    dist.destroy_process_group()
+
+
+def test_sharded_modes_equal_the_unsharded_run_gloo_world2():
+    g, z, cfg, sd = _setup()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for rank in (0, 1):
+        res = out[rank]
+        assert res["argmax"] == ([5.0, 2.0, 7.0], [2, 6, 9])
+        for mode in ("samples", "candidates"):
+            for ci in (1, 3):
+                adv, err, rows = res[(mode, ci)]
+                assert adv == g["cases"][ci]["adv"], (rank, mode, ci)
+                assert err < 1e-4
+    # each rank really did only its share of the work
+    c = g["cases"][1]
+    full = 2 * c["k"] * (c["B"] * c["n"] + c["B"])
+    assert out[0][("samples", 1)][2] + out[1][("samples", 1)][2] == full
+    assert out[0][("candidates", 1)][2] < 0.6 * full
