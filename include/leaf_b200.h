@@ -132,6 +132,18 @@ int leaf_encode(leaf_handle_t h, const int32_t* tok, const int32_t* len, const i
 int leaf_score(leaf_handle_t h, const float* feat, const float* anchor, int32_t B, int32_t n, int32_t objective,
                float* loss_out, int32_t* best_out, float* best_feat_out, void* stream);
 
+/* ---- K4: train-mode forward + backward of the selected adversarial batch -----------------------
+ * Replaces model.encode_text(adv_tokens) under autograd and loss.backward() of utils_AT.py:317-337 (the loss itself,
+ * mse(...).sum(-1).mean() on [B,E], stays a two-line torch expression on top of feat_out / dfeat).
+ * leaf_train_reserve sizes the activation store (and makes the [in,out] bf16 weight copies the dgrad products need);
+ * leaf_forward_train computes feat_out [N,E] fp32 and keeps every layer's activations (it synchronises the stream once
+ * to learn the packed row count); leaf_backward consumes dfeat [N,E] fp32 and ACCUMULATES (+=) the parameter
+ * gradients into the fp32 device buffers named by `grads` (same struct and layouts as leaf_bind_weights; a NULL
+ * pointer marks a frozen parameter). bf16 operands, fp32 accumulation, fp32 LayerNorm/softmax/activation math. */
+int leaf_train_reserve(leaf_handle_t h, int32_t max_seqs);
+int leaf_forward_train(leaf_handle_t h, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out, void* stream);
+int leaf_backward(leaf_handle_t h, const float* dfeat, const leaf_weight_ptrs_t* grads, void* stream);
+
 /* ---- test / bench hooks (used by tests/ and bench.py only) ------------------------------------ */
 /* C[M,N] = A[M,K] . Bt[N,K]^T (+bias[N]) with the tower's tcgen05 kernel. epilogue: 0 = bf16 store,
  * 1 = bf16 store after activation `act`, 2 = fp32 C += result (residual), 3 = fp32 store.

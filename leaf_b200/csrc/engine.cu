@@ -20,6 +20,7 @@
 #include "k1_tables_host.h"
 #include "k1_tokenize.cuh"
 #include "tower_kernels.cuh"
+#include "train_kernels.cuh"
 
 using namespace leaf;
 
@@ -48,8 +49,27 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct LayerW {
   __nv_bfloat16 *qkv_w = nullptr, *out_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;   // engine-owned bf16 copies
+  __nv_bfloat16 *qkv_wT = nullptr, *out_wT = nullptr, *fc1_wT = nullptr, *fc2_wT = nullptr;   // [in,out] copies for dgrad (K4)
   float* qkv_b_own = nullptr;                                                              // HF layout only
   const float* qkv_b = nullptr;
+};
+
+struct TrainLayer {        // activations one layer keeps for the backward pass (K4)
+  float *x_in = nullptr, *x_mid = nullptr;
+  __nv_bfloat16 *h1 = nullptr, *qkv = nullptr, *o = nullptr, *h2 = nullptr, *u = nullptr, *g = nullptr;
+};
+
+struct TrainWs {
+  int max_seqs = 0;
+  long rows_cap = 0;
+  int N = 0, M = 0;                   // sequences / packed rows of the saved forward
+  bool have_forward = false;
+  std::vector<TrainLayer> L;
+  float *x_out = nullptr, *dx = nullptr, *dtmp = nullptr, *scratch = nullptr;
+  __nv_bfloat16 *pooled = nullptr, *d16 = nullptr, *dx16 = nullptr, *t1 = nullptr, *t2 = nullptr;
+  int *tok = nullptr, *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr;
+  int4* meta = nullptr;
+  std::vector<void*> allocs;
 };
 
 struct leaf_engine {
@@ -67,6 +87,9 @@ struct leaf_engine {
   std::vector<leaf_layer_ptrs_t> layer_ptrs;
   std::vector<LayerW> lw;
   __nv_bfloat16* proj_w = nullptr;    // [E, W] bf16
+  __nv_bfloat16* proj_wT = nullptr;   // [W, E] bf16 (training: dgrad of the projection)
+  bool train_weights = false;         // transposed bf16 copies (dgrad operands) are kept
+  TrainWs tw;
   // workspace
   int max_seqs = 0;
   long rows_cap = 0;
@@ -188,6 +211,7 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_BF16_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTB_SMEM));
   *out = e;
   return LEAF_OK;
 }
@@ -205,10 +229,12 @@ static void free_workspace(leaf_engine* e) {
 static void free_weights(leaf_engine* e) {
   for (auto& l : e->lw) {
     cudaFree(l.qkv_w); cudaFree(l.out_w); cudaFree(l.fc1_w); cudaFree(l.fc2_w); cudaFree(l.qkv_b_own);
+    cudaFree(l.qkv_wT); cudaFree(l.out_wT); cudaFree(l.fc1_wT); cudaFree(l.fc2_wT);
   }
   e->lw.clear();
-  cudaFree(e->proj_w);
-  e->proj_w = nullptr;
+  cudaFree(e->proj_w); cudaFree(e->proj_wT);
+  e->proj_w = e->proj_wT = nullptr;
+  e->train_weights = false;
   e->bound = false;
   e->tmaps.clear();
 }
@@ -217,6 +243,8 @@ extern "C" int leaf_destroy(leaf_handle_t e) {
   if (!e) return LEAF_OK;
   cudaDeviceSynchronize();
   free_workspace(e);
+  for (void* p : e->tw.allocs) cudaFree(p);
+  e->tw = TrainWs();
   free_weights(e);
   for (void* p : e->table_allocs) cudaFree(p);
   for (auto& pr : e->gemm_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
@@ -269,6 +297,45 @@ static int cast_to(leaf_engine* e, const float* src, __nv_bfloat16* dst, size_t 
   return LEAF_OK;
 }
 
+static int cast_transpose_to(leaf_engine* e, const float* src, __nv_bfloat16* dst, int R, int C, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>((R + 31) / 32));
+  cast_bf16_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, R, C);
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+// [in,out] bf16 copies of the Linear weights: the K-major B operand of the dgrad products dX = dY . W
+static int refresh_transposed(leaf_engine* e, cudaStream_t st) {
+  const int W = e->cfg.width, E = e->cfg.embed_dim;
+  int rc;
+  for (int l = 0; l < e->cfg.layers; ++l) {
+    const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
+    LayerW& w = e->lw[l];
+    if (p.in_proj_w) {
+      if ((rc = cast_transpose_to(e, p.in_proj_w, w.qkv_wT, 3 * W, W, st))) return rc;       // [3W,W] -> [W,3W]
+    } else {                                                                                  // three [W,W] blocks side by side
+      const float* src[3] = {p.q_w, p.k_w, p.v_w};
+      for (int j = 0; j < 3; ++j) {
+        dim3 grid(static_cast<unsigned>((W + 31) / 32), static_cast<unsigned>((W + 31) / 32));
+        cast_bf16_transpose_ld_kernel<<<grid, dim3(32, 8), 0, st>>>(src[j], w.qkv_wT + j * W, W, W, 3 * W);
+        e->launches++;
+      }
+    }
+    if ((rc = cast_transpose_to(e, p.out_w, w.out_wT, W, W, st))) return rc;
+    if ((rc = cast_transpose_to(e, p.fc1_w, w.fc1_wT, 4 * W, W, st))) return rc;             // [4W,W] -> [W,4W]
+    if ((rc = cast_transpose_to(e, p.fc2_w, w.fc2_wT, W, 4 * W, st))) return rc;             // [W,4W] -> [4W,W]
+  }
+  // dpooled[N,W] = dfeat[N,E] . P^T  =>  Bt = P as [W,E]
+  if (e->wp.projection_is_ew) {
+    if ((rc = cast_transpose_to(e, e->wp.text_projection, e->proj_wT, E, W, st))) return rc;
+  } else {
+    if ((rc = cast_to(e, e->wp.text_projection, e->proj_wT, static_cast<size_t>(W) * E, st))) return rc;
+  }
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
 extern "C" int leaf_refresh_weights(leaf_handle_t e, void* stream) {
   if (!e || !e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -293,6 +360,9 @@ extern "C" int leaf_refresh_weights(leaf_handle_t e, void* stream) {
     if ((rc = cast_to(e, p.out_w, w.out_w, W * W, st))) return rc;
     if ((rc = cast_to(e, p.fc1_w, w.fc1_w, 4 * W * W, st))) return rc;
     if ((rc = cast_to(e, p.fc2_w, w.fc2_w, 4 * W * W, st))) return rc;
+  }
+  if (e->train_weights) {
+    if ((rc = refresh_transposed(e, st))) return rc;
   }
   if (e->wp.projection_is_ew) {
     if ((rc = cast_to(e, e->wp.text_projection, e->proj_w, E * W, st))) return rc;
@@ -505,4 +575,278 @@ extern "C" double leaf_timing_ms(leaf_handle_t e, int32_t which, int32_t* launch
   e->gemm_events.clear();
   if (launches) *launches = cnt;
   return total;
+}
+
+// =====================================================================================================================
+// K4: forward in train mode (activations kept) and backward of the selected adversarial batch
+// (/root/reference/utils_AT.py:312-337). Every product is a TN GEMM on the tcgen05 kernel:
+//   dgrad  dX[M,in]   = dY[M,out] . W[out,in]            -> A = dY (bf16),        Bt = W^T copy [in,out]
+//   wgrad  dW[out,in] += dY^T[out,M] . X[M,in]           -> A = dY^T [out,Mp],    Bt = X^T [in,Mp]   (fp32 accumulate into .grad)
+// =====================================================================================================================
+template <typename Tp>
+static int tw_alloc(TrainWs& t, Tp** p, size_t count) {
+  void* d = nullptr;
+  CK(cudaMalloc(&d, count * sizeof(Tp)));
+  t.allocs.push_back(d);
+  *p = static_cast<Tp*>(d);
+  return LEAF_OK;
+}
+
+static void free_train(leaf_engine* e) {
+  for (void* p : e->tw.allocs) cudaFree(p);
+  e->tw = TrainWs();
+  e->tmaps.clear();
+}
+
+extern "C" int leaf_train_reserve(leaf_handle_t e, int32_t max_seqs) {
+  if (!e || max_seqs <= 0) return fail(LEAF_ERR_INVALID, "max_seqs");
+  if (!e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
+  const size_t W = e->cfg.width, E = e->cfg.embed_dim;
+  int rc;
+  if (!e->train_weights) {
+    for (auto& l : e->lw) {
+      CK(cudaMalloc(&l.qkv_wT, 3 * W * W * 2));
+      CK(cudaMalloc(&l.out_wT, W * W * 2));
+      CK(cudaMalloc(&l.fc1_wT, 4 * W * W * 2));
+      CK(cudaMalloc(&l.fc2_wT, 4 * W * W * 2));
+    }
+    CK(cudaMalloc(&e->proj_wT, W * E * 2));
+    e->train_weights = true;
+    if ((rc = refresh_transposed(e, nullptr))) return rc;
+    CK(cudaDeviceSynchronize());
+  }
+  if (max_seqs <= e->tw.max_seqs) return LEAF_OK;
+  cudaDeviceSynchronize();
+  free_train(e);
+  TrainWs& t = e->tw;
+  const size_t rows = ((static_cast<size_t>(max_seqs) * LEAF_CTX + 127) / 128) * 128;
+  const size_t wide = 4 * W > E ? 4 * W : E;
+  t.L.resize(e->cfg.layers);
+  for (auto& l : t.L) {
+    if ((rc = tw_alloc(t, &l.x_in, rows * W))) return rc;
+    if ((rc = tw_alloc(t, &l.x_mid, rows * W))) return rc;
+    if ((rc = tw_alloc(t, &l.h1, rows * W))) return rc;
+    if ((rc = tw_alloc(t, &l.qkv, rows * 3 * W))) return rc;
+    if ((rc = tw_alloc(t, &l.o, rows * W))) return rc;
+    if ((rc = tw_alloc(t, &l.h2, rows * W))) return rc;
+    if ((rc = tw_alloc(t, &l.u, rows * 4 * W))) return rc;
+    if ((rc = tw_alloc(t, &l.g, rows * 4 * W))) return rc;
+  }
+  if ((rc = tw_alloc(t, &t.x_out, rows * W))) return rc;
+  if ((rc = tw_alloc(t, &t.dx, rows * W))) return rc;
+  if ((rc = tw_alloc(t, &t.dtmp, rows * wide))) return rc;
+  if ((rc = tw_alloc(t, &t.scratch, 2 * W))) return rc;
+  if ((rc = tw_alloc(t, &t.pooled, (static_cast<size_t>(max_seqs) + 128) * W))) return rc;
+  if ((rc = tw_alloc(t, &t.d16, rows * wide))) return rc;
+  if ((rc = tw_alloc(t, &t.dx16, rows * W))) return rc;
+  if ((rc = tw_alloc(t, &t.t1, wide * rows))) return rc;
+  if ((rc = tw_alloc(t, &t.t2, wide * rows))) return rc;
+  if ((rc = tw_alloc(t, &t.tok, static_cast<size_t>(max_seqs) * LEAF_CTX))) return rc;
+  if ((rc = tw_alloc(t, &t.cu, static_cast<size_t>(max_seqs) + 1))) return rc;
+  if ((rc = tw_alloc(t, &t.eos_row, static_cast<size_t>(max_seqs)))) return rc;
+  if ((rc = tw_alloc(t, &t.total_rows, 1))) return rc;
+  if ((rc = tw_alloc(t, &t.pfx, static_cast<size_t>(max_seqs)))) return rc;
+  if ((rc = tw_alloc(t, &t.own_len, static_cast<size_t>(max_seqs)))) return rc;
+  if ((rc = tw_alloc(t, &t.meta, static_cast<size_t>(max_seqs)))) return rc;
+  t.max_seqs = max_seqs;
+  t.rows_cap = static_cast<long>(rows);
+  return LEAF_OK;
+}
+
+static int launch_ew(leaf_engine* e, size_t n) {      // grid for the grid-stride element-wise kernels
+  size_t b = (n + 255) / 256;
+  const size_t cap = static_cast<size_t>(e->sm_count) * 16;
+  return static_cast<int>(b < cap ? (b ? b : 1) : cap);
+}
+
+extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out, void* stream) {
+  if (!e || !tok || !len || !feat_out || N <= 0) return fail(LEAF_ERR_INVALID, "bad argument");
+  if (!e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
+  if (N > e->tw.max_seqs) return fail(LEAF_ERR_STATE, "training workspace reserved for %d sequences, need %d (leaf_train_reserve)", e->tw.max_seqs, N);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  TrainWs& t = e->tw;
+  const int W = e->cfg.width, E = e->cfg.embed_dim, H = e->cfg.heads;
+  int rc;
+  t.have_forward = false;
+  CK(cudaMemcpyAsync(t.tok, tok, static_cast<size_t>(N) * LEAF_CTX * 4, cudaMemcpyDeviceToDevice, st));
+  prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, nullptr, N, t.pfx, t.own_len);
+  scan_lengths_kernel<<<1, 1024, 0, st>>>(t.own_len, N, t.cu, t.total_rows);
+  meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(t.cu, t.pfx, nullptr, N, t.meta, t.eos_row);
+  e->launches += 3;
+  int M = 0;
+  CK(cudaMemcpyAsync(&M, t.total_rows, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));                       // the packed row count sizes the wgrad contractions
+  if (M <= 0 || M > t.rows_cap) return fail(LEAF_ERR_STATE, "bad packed row count %d", M);
+  t.N = N; t.M = M;
+  embed_kernel<<<N, 256, 0, st>>>(tok, t.meta, N, W, e->wp.token_embedding, e->wp.positional_embedding, t.L[0].x_in);
+  e->launches++;
+  const size_t xbytes = static_cast<size_t>(M) * W * 4;
+  for (int l = 0; l < e->cfg.layers; ++l) {
+    const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
+    const LayerW& w = e->lw[l];
+    TrainLayer& a = t.L[l];
+    float* x_next = (l + 1 < e->cfg.layers) ? t.L[l + 1].x_in : t.x_out;
+    if ((rc = launch_layernorm(e, a.x_in, nullptr, M, nullptr, p.ln1_w, p.ln1_b, a.h1, st))) return rc;
+    if ((rc = launch_gemm(e, a.h1, t.rows_cap, w.qkv_w, w.qkv_b, a.qkv, 3 * W, M, 3 * W, W, EPI_BF16, 0, nullptr, st))) return rc;
+    attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(a.qkv, t.meta, N, H, W, a.o);
+    e->launches++;
+    CK(cudaMemcpyAsync(a.x_mid, a.x_in, xbytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_gemm(e, a.o, t.rows_cap, w.out_w, p.out_b, a.x_mid, W, M, W, W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    if ((rc = launch_layernorm(e, a.x_mid, nullptr, M, nullptr, p.ln2_w, p.ln2_b, a.h2, st))) return rc;
+    if ((rc = launch_gemm(e, a.h2, t.rows_cap, w.fc1_w, p.fc1_b, a.u, 4 * W, M, 4 * W, W, EPI_BF16, 0, nullptr, st))) return rc;
+    const size_t nu = static_cast<size_t>(M) * 4 * W;
+    act_fwd_kernel<<<launch_ew(e, nu), 256, 0, st>>>(a.u, a.g, nu, e->cfg.activation);
+    e->launches++;
+    CK(cudaMemcpyAsync(x_next, a.x_mid, xbytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_gemm(e, a.g, t.rows_cap, w.fc2_w, p.fc2_b, x_next, W, M, W, 4 * W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+  }
+  if ((rc = launch_layernorm(e, t.x_out, nullptr, N, t.eos_row, e->wp.lnf_w, e->wp.lnf_b, t.pooled, st))) return rc;
+  if ((rc = launch_gemm(e, t.pooled, t.max_seqs + 128, e->proj_w, nullptr, feat_out, E, N, E, W, EPI_F32, 0, nullptr, st))) return rc;
+  CK(cudaGetLastError());
+  t.have_forward = true;
+  return LEAF_OK;
+}
+
+template <typename Tp>
+static int launch_transpose(leaf_engine* e, const Tp* src, __nv_bfloat16* dst, int R, int C, int Rp, cudaStream_t st) {
+  dim3 grid(static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>((Rp + 31) / 32));
+  transpose_bf16_kernel<Tp><<<grid, dim3(32, 8), 0, st>>>(src, dst, R, C, Rp);
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+template <typename Tp>
+static int launch_colsum(leaf_engine* e, const Tp* src, int R, int C, int ld, float* dst, cudaStream_t st) {
+  if (!dst) return LEAF_OK;
+  int gy = (R + 255) / 256;
+  if (gy > 64) gy = 64;
+  colsum_kernel<Tp><<<dim3((C + 31) / 32, gy), 256, 0, st>>>(src, R, C, ld, dst);
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x, const int* gather, int rows, const float* gamma,
+                                float* dx, int accumulate, float* dgamma, float* dbeta, float* scratch, cudaStream_t st) {
+  const int W = e->cfg.width;
+  // frozen LayerNorm parameters (NULL grads) still need somewhere to add to: the scratch row pair
+  if (!dgamma) dgamma = scratch;
+  if (!dbeta) dbeta = scratch + W;
+  int blocks = (rows + 7) / 8;
+  if (blocks > e->sm_count * 2) blocks = e->sm_count * 2;
+  if (blocks < 1) blocks = 1;
+#define LNB_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gather, rows, W, gamma, e->cfg.ln_eps, dx, accumulate, dgamma, dbeta); break;
+  switch (W / 128) {
+    LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
+    LNB_CASE(9) LNB_CASE(10) LNB_CASE(11) LNB_CASE(12) LNB_CASE(13) LNB_CASE(14) LNB_CASE(15) LNB_CASE(16)
+    default: return fail(LEAF_ERR_INVALID, "unsupported width %d", W);
+  }
+#undef LNB_CASE
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+// grads mirrors leaf_weight_ptrs_t: fp32 device buffers that are ACCUMULATED into (+=); NULL = parameter is frozen.
+extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_weight_ptrs_t* grads, void* stream) {
+  if (!e || !dfeat || !grads || !grads->layers) return fail(LEAF_ERR_INVALID, "null argument");
+  TrainWs& t = e->tw;
+  if (!t.have_forward) return fail(LEAF_ERR_STATE, "leaf_backward needs a preceding leaf_forward_train");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int W = e->cfg.width, E = e->cfg.embed_dim, H = e->cfg.heads, N = t.N, M = t.M;
+  const int Mp = (M + 7) & ~7, Np = (N + 7) & ~7;
+  const long cap = t.rows_cap;
+  int rc;
+  auto F = [](const float* p) { return const_cast<float*>(p); };
+  float* scratch = t.scratch;                        // sink for the LayerNorm gradients of frozen parameters
+  // ---- projection + ln_final on the pooled rows ----
+  const size_t nfe = static_cast<size_t>(N) * E;
+  cast_f32_bf16_kernel<<<launch_ew(e, nfe), 256, 0, st>>>(dfeat, t.d16, nfe);
+  e->launches++;
+  if ((rc = launch_gemm(e, t.d16, N, e->proj_wT, nullptr, t.dtmp, W, N, W, E, EPI_F32, 0, nullptr, st))) return rc;      // dpooled [N,W]
+  if (grads->text_projection) {
+    if ((rc = launch_transpose(e, t.pooled, t.t1, N, W, Np, st))) return rc;                                             // pooled^T [W,Np]
+    if ((rc = launch_transpose(e, dfeat, t.t2, N, E, Np, st))) return rc;                                                // dfeat^T  [E,Np]
+    if (grads->projection_is_ew) {
+      if ((rc = launch_gemm(e, t.t2, E, t.t1, nullptr, F(grads->text_projection), W, E, W, Np, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    } else {
+      if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(grads->text_projection), E, W, E, Np, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    }
+  }
+  CK(cudaMemsetAsync(t.dx, 0, static_cast<size_t>(M) * W * 4, st));
+  CK(cudaMemsetAsync(scratch, 0, 2 * W * 4, st));
+  if ((rc = launch_layernorm_bwd(e, t.dtmp, t.x_out, t.eos_row, N, e->wp.lnf_w, t.dx, 0, F(grads->lnf_w), F(grads->lnf_b), scratch, st))) return rc;
+  const size_t nx = static_cast<size_t>(M) * W;
+  for (int l = e->cfg.layers - 1; l >= 0; --l) {
+    const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
+    const leaf_layer_ptrs_t& g = grads->layers[l];
+    const LayerW& w = e->lw[l];
+    TrainLayer& a = t.L[l];
+    // ================= MLP branch: x_next = x_mid + fc2(act(fc1(ln_2(x_mid)))) =================
+    cast_f32_bf16_kernel<<<launch_ew(e, nx), 256, 0, st>>>(t.dx, t.dx16, nx);
+    e->launches++;
+    if ((rc = launch_gemm(e, t.dx16, cap, w.fc2_wT, nullptr, t.dtmp, 4 * W, M, 4 * W, W, EPI_F32, 0, nullptr, st))) return rc;   // dg [M,4W]
+    if (g.fc2_w) {
+      if ((rc = launch_transpose(e, t.dx, t.t1, M, W, Mp, st))) return rc;                                                 // dx^T [W,Mp]
+      if ((rc = launch_transpose(e, a.g, t.t2, M, 4 * W, Mp, st))) return rc;                                              // g^T [4W,Mp]
+      if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(g.fc2_w), 4 * W, W, 4 * W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    }
+    if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.fc2_b), st))) return rc;
+    const size_t nu = static_cast<size_t>(M) * 4 * W;
+    act_bwd_kernel<<<launch_ew(e, nu), 256, 0, st>>>(t.dtmp, a.u, t.d16, nu, e->cfg.activation);                           // du [M,4W] bf16
+    e->launches++;
+    if ((rc = launch_gemm(e, t.d16, cap, w.fc1_wT, nullptr, t.dtmp, W, M, W, 4 * W, EPI_F32, 0, nullptr, st))) return rc;        // dh2 [M,W]
+    if (g.fc1_w) {
+      if ((rc = launch_transpose(e, t.d16, t.t1, M, 4 * W, Mp, st))) return rc;                                            // du^T [4W,Mp]
+      if ((rc = launch_transpose(e, a.h2, t.t2, M, W, Mp, st))) return rc;                                                 // h2^T [W,Mp]
+      if ((rc = launch_gemm(e, t.t1, 4 * W, t.t2, nullptr, F(g.fc1_w), W, 4 * W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    }
+    if ((rc = launch_colsum(e, t.d16, M, 4 * W, 4 * W, F(g.fc1_b), st))) return rc;
+    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_mid, nullptr, M, p.ln2_w, t.dx, 1, F(g.ln2_w), F(g.ln2_b), scratch, st))) return rc;
+    // ================= attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in)))) =================
+    cast_f32_bf16_kernel<<<launch_ew(e, nx), 256, 0, st>>>(t.dx, t.dx16, nx);
+    e->launches++;
+    if ((rc = launch_gemm(e, t.dx16, cap, w.out_wT, nullptr, t.dtmp, W, M, W, W, EPI_F32, 0, nullptr, st))) return rc;           // do [M,W]
+    if (g.out_w) {
+      if ((rc = launch_transpose(e, t.dx, t.t1, M, W, Mp, st))) return rc;
+      if ((rc = launch_transpose(e, a.o, t.t2, M, W, Mp, st))) return rc;
+      if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(g.out_w), W, W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    }
+    if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.out_b), st))) return rc;
+    attention_bwd_kernel<<<dim3(N, H), ATTB_THREADS, ATTB_SMEM, st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.d16);               // dqkv [M,3W] bf16
+    e->launches++;
+    CK(cudaGetLastError());
+    if ((rc = launch_gemm(e, t.d16, cap, w.qkv_wT, nullptr, t.dtmp, W, M, W, 3 * W, EPI_F32, 0, nullptr, st))) return rc;        // dh1 [M,W]
+    const bool fused = g.in_proj_w != nullptr;
+    if (fused || g.q_w || g.k_w || g.v_w) {
+      if ((rc = launch_transpose(e, t.d16, t.t1, M, 3 * W, Mp, st))) return rc;                                            // dqkv^T [3W,Mp]
+      if ((rc = launch_transpose(e, a.h1, t.t2, M, W, Mp, st))) return rc;                                                 // h1^T [W,Mp]
+      if (fused) {
+        if ((rc = launch_gemm(e, t.t1, 3 * W, t.t2, nullptr, F(g.in_proj_w), W, 3 * W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+      } else {
+        const float* dst[3] = {g.q_w, g.k_w, g.v_w};
+        for (int j = 0; j < 3; ++j)
+          if (dst[j] && (rc = launch_gemm(e, t.t1 + static_cast<size_t>(j) * W * Mp, W, t.t2, nullptr, F(dst[j]), W, W, W, Mp,
+                                          EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+      }
+    }
+    if (fused) {
+      if ((rc = launch_colsum(e, t.d16, M, 3 * W, 3 * W, F(g.in_proj_b), st))) return rc;
+    } else {
+      const float* dst[3] = {g.q_b, g.k_b, g.v_b};
+      for (int j = 0; j < 3; ++j)
+        if ((rc = launch_colsum(e, t.d16 + j * W, M, W, 3 * W, F(dst[j]), st))) return rc;
+    }
+    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_in, nullptr, M, p.ln1_w, t.dx, 1, F(g.ln1_w), F(g.ln1_b), scratch, st))) return rc;
+  }
+  if (grads->token_embedding || grads->positional_embedding) {
+    // a frozen table still needs a target for the atomics: reuse dtmp as a sink is not possible (49408 rows) -> require both
+    if (!grads->token_embedding || !grads->positional_embedding)
+      return fail(LEAF_ERR_INVALID, "token and positional embedding gradients must be given together");
+    embed_bwd_kernel<<<N, 256, 0, st>>>(t.tok, t.meta, N, W, t.dx, F(grads->token_embedding), F(grads->positional_embedding));
+    e->launches++;
+  }
+  CK(cudaGetLastError());
+  return LEAF_OK;
 }

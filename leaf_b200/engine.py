@@ -134,16 +134,19 @@ class LeafEngine:
         if self.width != self.heads * 64:
             raise LeafError(f"head_dim must be 64 (width {self.width}, heads {self.heads})")
 
-    def _bind(self):
-        c = self._canon
+    def _make_ptrs(self, c):
+        """leaf_weight_ptrs_t over a canonical dict of tensors (None entries become NULL)."""
+        dp = lambda t: None if t is None else t.data_ptr()
         arr = (LeafLayerPtrs * self.layers)()
         for i, l in enumerate(c["layers"]):
             for k, _ in LeafLayerPtrs._fields_:
-                setattr(arr[i], k, l[k].data_ptr() if k in l else None)
-        wp = LeafWeightPtrs(c["tok"].data_ptr(), c["pos"].data_ptr(), c["lnf_w"].data_ptr(), c["lnf_b"].data_ptr(),
-                            c["proj"].data_ptr(), c["proj_is_ew"], arr)
-        self._keep = (arr, wp)
-        check(self._lib.leaf_bind_weights(self._h, ctypes.byref(wp), _stream()))
+                setattr(arr[i], k, dp(l.get(k)))
+        wp = LeafWeightPtrs(dp(c["tok"]), dp(c["pos"]), dp(c["lnf_w"]), dp(c["lnf_b"]), dp(c["proj"]), c["proj_is_ew"], arr)
+        return arr, wp
+
+    def _bind(self):
+        self._keep = self._make_ptrs(self._canon)
+        check(self._lib.leaf_bind_weights(self._h, ctypes.byref(self._keep[1]), _stream()))
 
     def refresh_weights(self):
         """Re-cast the bf16 operand copies from the live fp32 parameters (after optimizer.step())."""
@@ -230,6 +233,30 @@ class LeafEngine:
             check(self._lib.leaf_encode(self._h, _ptr(tok), _ptr(lengths.contiguous()), _ptr(base), N, 1 if normalize else 0,
                                         _ptr(out), _stream()))
         return out
+
+    # ---- K4 ----------------------------------------------------------------------------------------------
+    def forward_train(self, tok: torch.Tensor, lengths: torch.Tensor = None) -> torch.Tensor:
+        """encode_text in train mode (utils_AT.py:317-319): same features, every layer's activations are kept."""
+        tok = tok.to(torch.int32).contiguous()
+        N = tok.shape[0]
+        if lengths is None:
+            lengths = (tok.argmax(dim=-1) + 1).to(torch.int32)
+        out = torch.empty((N, self.embed_dim), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_train_reserve(self._h, N))
+            check(self._lib.leaf_forward_train(self._h, _ptr(tok), _ptr(lengths.contiguous()), N, _ptr(out), _stream()))
+        return out
+
+    def backward(self, dfeat: torch.Tensor, grads: dict):
+        """loss.backward() through the saved forward: ACCUMULATES into the fp32 tensors of `grads`, a dict in the same
+        naming as the bound parameters (open_clip or HF); entries that are None mark frozen parameters."""
+        c = _canon_state(grads)
+        for t in [c["tok"], c["pos"], c["lnf_w"], c["lnf_b"], c["proj"]] + [t for l in c["layers"] for t in l.values()]:
+            if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise LeafError("gradient buffers must be contiguous fp32 CUDA tensors")
+        keep = self._make_ptrs(c)
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_backward(self._h, _ptr(dfeat.to(torch.float32).contiguous()), ctypes.byref(keep[1]), _stream()))
 
     # ---- K3 ----------------------------------------------------------------------------------------------
     def score(self, feats: torch.Tensor, anchor: torch.Tensor, B: int, n: int, objective: str = "l2", want_loss=False):

@@ -12,6 +12,25 @@ from . import synth
 from .engine import LeafEngine
 
 
+class _EncodeTextTrain(torch.autograd.Function):
+    """encode_text under autograd: forward = leaf_forward_train, backward = leaf_backward. The parameters are inputs of
+    the Function so that autograd accumulates the returned gradients into their .grad, like any torch module."""
+
+    @staticmethod
+    def forward(ctx, tower, tok, *params):
+        ctx.tower = tower
+        ctx.needs = [p.requires_grad for p in params]
+        return tower.leaf_engine.forward_train(tok)
+
+    @staticmethod
+    def backward(ctx, dfeat):
+        tower = ctx.tower
+        names = list(tower._names)
+        grads = {k: torch.zeros_like(getattr(tower, tower._names[k]).data) for k in names}
+        tower.leaf_engine.backward(dfeat, grads)
+        return (None, None) + tuple(grads[k] if need else None for k, need in zip(names, ctx.needs))
+
+
 class LeafTextTower(torch.nn.Module):
     def __init__(self, state_dict: dict, heads: int, quick_gelu: bool = False, device="cuda"):
         super().__init__()
@@ -41,6 +60,19 @@ class LeafTextTower(torch.nn.Module):
     def tokenizer(self, texts):
         return self.leaf_engine.tokenize(texts)
 
-    @torch.no_grad()
+    def trainable(self, on: bool = True):
+        """Mark the tower's parameters as requiring gradients (the attacked tower in train_AT_text_only.py)."""
+        for p in self.parameters():
+            p.requires_grad_(on)
+        return self
+
     def encode_text(self, text, normalize: bool = False):
-        return self.leaf_engine.encode_tokens(text, None, normalize)
+        """model.py:269-284. Under torch.no_grad() (the attack, utils_AT.py:295) this is the inference path; with
+        gradients enabled and trainable parameters (utils_AT.py:317-319) the forward keeps its activations and
+        loss.backward() runs the engine's backward. Call refresh() after optimizer.step()."""
+        params = [getattr(self, safe) for safe in self._names.values()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            f = _EncodeTextTrain.apply(self, text, *params)
+            return torch.nn.functional.normalize(f, dim=-1) if normalize else f
+        with torch.no_grad():
+            return self.leaf_engine.encode_tokens(text, None, normalize)

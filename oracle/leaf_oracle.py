@@ -228,6 +228,32 @@ def encode_text(sd: dict, tokens: torch.Tensor, heads: int, quick_gelu: bool = F
     return F.normalize(out, dim=-1) if normalize else out
 
 
+def encode_text_device(sd: dict, tokens: torch.Tensor, heads: int, quick_gelu: bool = False) -> torch.Tensor:
+    """encode_text above without the .float() copies and on the parameters' device, so that torch autograd can
+    differentiate it (reference gradients for the K4 tests; same lines of model.py / transformer.py)."""
+    tokens = tokens.long()
+    N, T = tokens.shape
+    x = sd["token_embedding.weight"][tokens] + sd["positional_embedding"][:T]
+    W = x.shape[-1]
+    d = W // heads
+    mask = torch.full((T, T), float("-inf"), device=x.device).triu_(1)
+    i = 0
+    while f"transformer.resblocks.{i}.ln_1.weight" in sd:
+        p = f"transformer.resblocks.{i}."
+        h = F.layer_norm(x, (W,), sd[p + "ln_1.weight"], sd[p + "ln_1.bias"], 1e-5)
+        qkv = h @ sd[p + "attn.in_proj_weight"].T + sd[p + "attn.in_proj_bias"]
+        q, k, v = (z.view(N, T, heads, d).transpose(1, 2) for z in qkv.split(W, dim=-1))
+        att = torch.softmax((q @ k.transpose(-1, -2)) * (d ** -0.5) + mask, dim=-1)
+        o = (att @ v).transpose(1, 2).reshape(N, T, W)
+        x = x + o @ sd[p + "attn.out_proj.weight"].T + sd[p + "attn.out_proj.bias"]
+        h = F.layer_norm(x, (W,), sd[p + "ln_2.weight"], sd[p + "ln_2.bias"], 1e-5)
+        h = _act(h @ sd[p + "mlp.c_fc.weight"].T + sd[p + "mlp.c_fc.bias"], quick_gelu)
+        x = x + h @ sd[p + "mlp.c_proj.weight"].T + sd[p + "mlp.c_proj.bias"]
+        i += 1
+    x = F.layer_norm(x, (W,), sd["ln_final.weight"], sd["ln_final.bias"], 1e-5)
+    return x[torch.arange(N, device=x.device), tokens.argmax(dim=-1)] @ sd["text_projection"]
+
+
 # ----------------------------------------------------------------------------------------------
 # loss / argmax and the attack driver
 # ----------------------------------------------------------------------------------------------
