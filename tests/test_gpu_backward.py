@@ -1,6 +1,9 @@
 """K4 on the GPU: gradients of the FARE objective (utils_AT.py:317-337) through the engine's backward against torch
-autograd over the fp32 oracle tower, for the open_clip and the HF parameter layouts. Tolerance: the engine multiplies
-bf16 operands (the reference trains under fp16 autocast); relative L2 error per tensor <= 3e-2, cosine >= 0.999."""
+autograd over the fp32 oracle tower, for the open_clip and the HF parameter layouts.
+Tolerances (the engine multiplies bf16 operands; the reference trains under fp16 autocast):
+  * backward alone (same cotangent dL/df fed to both): relative L2 error per tensor <= 3e-2, cosine >= 0.999;
+  * end to end (loss.backward()): the TextFARE cotangent 2(f - a)/B is a DIFFERENCE of embeddings, so the forward's
+    bf16 error (|df|/|f| ~ 7e-3) is amplified by |f|/|f - a| before it enters the backward: cosine >= 0.995."""
 import numpy as np
 import pytest
 import torch
@@ -8,12 +11,16 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-def _ref_grads(sd, tok, anchor, heads, quick):
+def _ref_grads(sd, tok, anchor, heads, quick, cotangent=None):
+    """fp32 autograd reference. cotangent = None: gradients of the FARE loss; else the vector-Jacobian product."""
     from oracle import leaf_oracle as O
     p = {k: v.detach().clone().cuda().requires_grad_(True) for k, v in sd.items()}
     f = O.encode_text_device(p, tok.cuda(), heads, quick_gelu=quick)
     loss = torch.nn.functional.mse_loss(anchor, f, reduction="none").sum(-1).mean()      # utils_AT.py:321
-    loss.backward()
+    if cotangent is None:
+        loss.backward()
+    else:
+        f.backward(cotangent)
     return loss.item(), f.detach(), {k: v.grad for k, v in p.items()}
 
 
@@ -35,19 +42,25 @@ def test_backward_matches_autograd(name, quick):
     loss.backward()
     ref_loss, ref_f, ref = _ref_grads(sd, tok, anchor, cfg.heads, quick)
     assert abs(loss.item() - ref_loss) <= 1e-2 * abs(ref_loss)
-    worst = {}
-    for k, safe in tower._names.items():
-        got, want = getattr(tower, safe).grad, ref[k]
-        assert got is not None and got.shape == want.shape, k
+    cot = (2.0 * (f.detach() - anchor) / len(caps)).contiguous()            # the cotangent the engine's backward was given
+    _, _, vjp = _ref_grads(sd, tok, anchor, cfg.heads, quick, cotangent=cot)
+
+    def err(got, want):
         rel = ((got - want).norm() / want.norm().clamp_min(1e-20)).item()
-        cos = torch.nn.functional.cosine_similarity(got.flatten().double(), want.flatten().double(), dim=0).item()
-        worst[k] = (rel, cos)
-        assert rel <= 3e-2 and cos >= 0.999, (k, rel, cos)
+        return rel, torch.nn.functional.cosine_similarity(got.flatten().double(), want.flatten().double(), dim=0).item()
+
+    for k, safe in tower._names.items():
+        got = getattr(tower, safe).grad
+        assert got is not None and got.shape == ref[k].shape, k
+        rel, cos = err(got, vjp[k])
+        assert rel <= 3e-2 and cos >= 0.999, ("backward", k, rel, cos)
+        rel, cos = err(got, ref[k])
+        assert cos >= 0.995, ("end to end", k, rel, cos)
     # a second backward accumulates (+=) like torch
     f2 = tower.encode_text(tok)
     torch.nn.functional.mse_loss(anchor, f2, reduction="none").sum(-1).mean().backward()
     k0 = "transformer.resblocks.0.mlp.c_fc.weight"
-    assert torch.allclose(getattr(tower, tower._names[k0]).grad, 2 * ref[k0], rtol=5e-2, atol=1e-6)
+    assert err(getattr(tower, tower._names[k0]).grad, 2 * vjp[k0])[0] <= 3e-2
 
 
 def test_backward_hf_layout():
@@ -72,7 +85,10 @@ def test_backward_hf_layout():
     tok = e1.tokenize(synth.make_captions(5, seed=1))
     f1, f2 = e1.forward_train(tok), e2.forward_train(tok)
     assert torch.equal(f1, f2)
-    assert torch.equal(f1, e1.encode_tokens(tok))                 # train-mode forward == inference forward (no dropout)
+    # train-mode forward == inference forward (no dropout in the text tower); the two paths round fc1's output at
+    # different points (fused GELU epilogue vs saved pre-activation), hence a bf16-level tolerance
+    fi = e1.encode_tokens(tok)
+    assert (f1 - fi).norm() / fi.norm() < 1e-2
     d = torch.randn_like(f1)
     g1 = {k: torch.zeros_like(v) for k, v in sd.items()}
     g2 = {k: torch.zeros_like(v) for k, v in hf.items()}
