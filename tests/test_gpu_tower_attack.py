@@ -193,3 +193,39 @@ def test_attack_full_config_vs_oracle_scores():
     top = torch.topk(want_loss, 2, dim=-1).values
     nontied = (top[:, 0] - top[:, 1]).abs() > LOSS_RTOL * top[:, 0].abs()
     assert torch.equal(best.cpu().long()[nontied], want_loss.argmax(-1)[nontied])
+
+
+def test_full_size_properties_vit_h():
+    """BASELINE config size (ViT-H-14 text tower, B=128, rho=50): the fp32 oracle cannot run 12 800 ViT-H encodes in
+    seconds, so parity at full size rests on size-independent properties: shared-prefix packing is bit-identical to
+    encoding every row on its own, duplicate candidates tie exactly, K3's loss/argmax equal torch on the same
+    features, and the attack's winners are the argmax of their own phase."""
+    from leaf_b200 import synth
+    from leaf_b200.tower import LeafTextTower
+    tower = LeafTextTower.random("ViT-H-14", seed=0)
+    eng = tower.leaf_engine
+    B, n = 128, 50
+    caps = synth.make_captions(B - 8, seed=0) + synth.make_captions(8, seed=0, kind="dense-77")
+    rs = np.random.RandomState(0)
+    pos = np.stack([rs.choice(range(2 * len(S) + 1), size=n, replace=False) for S in caps]).astype(np.int32)
+    chr_ = np.array(synth.V_DEFAULT, dtype=np.int32)[rs.randint(0, 96, size=(B, n))]
+    chr_[:, 7] = chr_[:, 3]                                   # forced duplicates (same position below, same character)
+    pos[:, 7] = pos[:, 3]
+    d, o = eng.upload_captions(caps)
+    tok, ln, base = eng.expand_tokenize(d, o, B, n, torch.from_numpy(pos).cuda(), torch.from_numpy(chr_).cuda())
+    assert torch.equal(tok.view(-1, 77)[:B * n].view(B, n, 77)[:, 7], tok[:B * n].view(B, n, 77)[:, 3])
+    shared = eng.encode_tokens(tok, ln, False, base)
+    rows_shared = eng.last_rows()
+    plain = eng.encode_tokens(tok, ln, False, None)
+    assert eng.last_rows() == int(ln.sum()) and rows_shared < eng.last_rows()
+    assert torch.equal(shared, plain)
+    assert torch.isfinite(shared).all()
+    f = shared[:B * n].view(B, n, -1)
+    assert torch.equal(f[:, 7], f[:, 3])
+    anchor = shared[B * n:] + 0.01 * torch.randn((B, f.shape[-1]), generator=torch.Generator().manual_seed(1)).cuda()
+    best, bf, loss = eng.score(shared, anchor, B, n, "l2", want_loss=True)
+    ref = ((f - anchor.view(B, 1, -1)) ** 2).sum(-1)
+    assert torch.allclose(loss, ref, rtol=1e-4, atol=1e-6)
+    assert torch.equal(best.long(), loss.argmax(-1))
+    assert torch.equal(loss[:, 7], loss[:, 3]) and not (best == 7).any()      # first index wins exact ties
+    assert torch.equal(bf, f[torch.arange(B), best.long()])
