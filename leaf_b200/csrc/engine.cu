@@ -62,7 +62,7 @@ struct TrainLayer {        // activations one layer keeps for the backward pass 
 struct TrainWs {
   int max_seqs = 0;
   long rows_cap = 0;
-  int N = 0, M = 0;                   // sequences / packed rows of the saved forward
+  int N = 0, M = 0, T = 0;            // sequences / packed rows / longest sequence of the saved forward
   bool have_forward = false;
   std::vector<TrainLayer> L;
   float *x_out = nullptr, *dx = nullptr, *dtmp = nullptr, *scratch = nullptr;
@@ -211,7 +211,7 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_BF16_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTB_SMEM));
+  CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attb_smem_bytes(LEAF_CTX)));
   *out = e;
   return LEAF_OK;
 }
@@ -644,7 +644,7 @@ extern "C" int leaf_train_reserve(leaf_handle_t e, int32_t max_seqs) {
   if ((rc = tw_alloc(t, &t.tok, static_cast<size_t>(max_seqs) * LEAF_CTX))) return rc;
   if ((rc = tw_alloc(t, &t.cu, static_cast<size_t>(max_seqs) + 1))) return rc;
   if ((rc = tw_alloc(t, &t.eos_row, static_cast<size_t>(max_seqs)))) return rc;
-  if ((rc = tw_alloc(t, &t.total_rows, 1))) return rc;
+  if ((rc = tw_alloc(t, &t.total_rows, 2))) return rc;
   if ((rc = tw_alloc(t, &t.pfx, static_cast<size_t>(max_seqs)))) return rc;
   if ((rc = tw_alloc(t, &t.own_len, static_cast<size_t>(max_seqs)))) return rc;
   if ((rc = tw_alloc(t, &t.meta, static_cast<size_t>(max_seqs)))) return rc;
@@ -670,14 +670,15 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
   t.have_forward = false;
   CK(cudaMemcpyAsync(t.tok, tok, static_cast<size_t>(N) * LEAF_CTX * 4, cudaMemcpyDeviceToDevice, st));
   prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, nullptr, N, t.pfx, t.own_len);
-  scan_lengths_kernel<<<1, 1024, 0, st>>>(t.own_len, N, t.cu, t.total_rows);
+  scan_lengths_kernel<<<1, 1024, 0, st>>>(t.own_len, N, t.cu, t.total_rows, t.total_rows + 1);
   meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(t.cu, t.pfx, nullptr, N, t.meta, t.eos_row);
   e->launches += 3;
-  int M = 0;
-  CK(cudaMemcpyAsync(&M, t.total_rows, 4, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));                       // the packed row count sizes the wgrad contractions
-  if (M <= 0 || M > t.rows_cap) return fail(LEAF_ERR_STATE, "bad packed row count %d", M);
-  t.N = N; t.M = M;
+  int mt[2] = {0, 0};
+  CK(cudaMemcpyAsync(mt, t.total_rows, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));                       // packed row count (sizes the wgrad contractions) + longest sequence
+  const int M = mt[0];
+  if (M <= 0 || M > t.rows_cap || mt[1] <= 0 || mt[1] > LEAF_CTX) return fail(LEAF_ERR_STATE, "bad packed row count %d / length %d", M, mt[1]);
+  t.N = N; t.M = M; t.T = mt[1];
   embed_kernel<<<N, 256, 0, st>>>(tok, t.meta, N, W, e->wp.token_embedding, e->wp.positional_embedding, t.L[0].x_in);
   e->launches++;
   const size_t xbytes = static_cast<size_t>(M) * W * 4;
@@ -734,7 +735,7 @@ static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x,
   if (!dgamma) dgamma = scratch;
   if (!dbeta) dbeta = scratch + W;
   int blocks = (rows + 7) / 8;
-  if (blocks > e->sm_count * 2) blocks = e->sm_count * 2;
+  if (blocks > e->sm_count) blocks = e->sm_count;
   if (blocks < 1) blocks = 1;
 #define LNB_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gather, rows, W, gamma, e->cfg.ln_eps, dx, accumulate, dgamma, dbeta); break;
   switch (W / 128) {
@@ -814,7 +815,7 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
       if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(g.out_w), W, W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
     }
     if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.out_b), st))) return rc;
-    attention_bwd_kernel<<<dim3(N, H), ATTB_THREADS, ATTB_SMEM, st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.d16);               // dqkv [M,3W] bf16
+    attention_bwd_kernel<<<dim3(N, H), ATTB_THREADS, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16);   // dqkv [M,3W] bf16
     e->launches++;
     CK(cudaGetLastError());
     if ((rc = launch_gemm(e, t.d16, cap, w.qkv_wT, nullptr, t.dtmp, W, M, W, 3 * W, EPI_F32, 0, nullptr, st))) return rc;        // dh1 [M,W]

@@ -9,12 +9,12 @@
 //
 // This header holds the PTX wrappers, descriptors and the fused epilogue; the kernel itself (CTA-pair,
 // cta_group::2) is gemm2_sm100.cuh. Roles per CTA (640 threads):
-//   warp 0      TMA producer   : cp.async.bulk.tensor, 128B-swizzled 128x64 boxes of A and B into a shared-memory
+//   warp 16     TMA producer   : cp.async.bulk.tensor, 128B-swizzled 128x64 boxes of A and B into a shared-memory
 //                                ring, completion on mbarriers
-//   warp 1      MMA issuer     : one thread (leader CTA) issues tcgen05.mma.kind::f16, accumulators in TMEM,
+//   warp 17     MMA issuer     : one thread (leader CTA) issues tcgen05.mma.kind::f16, accumulators in TMEM,
 //                                double buffered (2 x 256 columns)
-//   warp 2      TMEM allocator
-//   warps 4-19  epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> fused bias / GELU / residual
+//   warp 18     TMEM allocator
+//   warps 0-15  epilogue       : tcgen05.ld 32 lanes x 32 columns -> registers -> fused bias / GELU / residual
 //                                -> coalesced global store; overlaps the next tile's MMAs (TMEM double buffer)
 // M may be a device-side value (packed token rows are only known on the device).
 #pragma once

@@ -23,15 +23,17 @@ __device__ __forceinline__ float warp_max(float v) {
 // exclusive scan of the row lengths -> cu[N+1]; also clamps len to [1, 77]. Single CTA (N <= ~10^5).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int* __restrict__ len, int N, int* __restrict__ cu,
-                                                            int* __restrict__ total_rows) {
+                                                            int* __restrict__ total_rows, int* __restrict__ max_len = nullptr) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
-  if (threadIdx.x == 0) carry = 0;
+  __shared__ int vmax_s;
+  if (threadIdx.x == 0) { carry = 0; vmax_s = 0; }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = 0; base < N; base += 1024) {
     const int i = base + threadIdx.x;
     int v = (i < N) ? min(max(len[i], 1), 77) : 0;
+    if (max_len) atomicMax(&vmax_s, v);
     int inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -60,6 +62,7 @@ __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int* __restric
   if (threadIdx.x == 0) {
     cu[N] = carry;
     *total_rows = carry;
+    if (max_len) *max_len = vmax_s;
   }
 }
 

@@ -149,12 +149,25 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       out[lane + 32 * i] = o;
     }
   }
+  // CTA-level reduction (warps take turns on a shared accumulator), then ONE atomic per column and CTA
+  __shared__ float red[2][VPL * 128];
+  for (int c = threadIdx.x; c < 2 * VPL * 128; c += blockDim.x) (&red[0][0])[c] = 0.f;
+  __syncthreads();
+  for (int w = 0; w < (blockDim.x >> 5); ++w) {
+    if ((threadIdx.x >> 5) == w) {
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    float* dgp = dgamma + (lane + 32 * i) * 4;
-    float* dbp = dbeta + (lane + 32 * i) * 4;
-    atomicAdd(dgp, dg_acc[i].x); atomicAdd(dgp + 1, dg_acc[i].y); atomicAdd(dgp + 2, dg_acc[i].z); atomicAdd(dgp + 3, dg_acc[i].w);
-    atomicAdd(dbp, db_acc[i].x); atomicAdd(dbp + 1, db_acc[i].y); atomicAdd(dbp + 2, db_acc[i].z); atomicAdd(dbp + 3, db_acc[i].w);
+      for (int i = 0; i < VPL; ++i) {
+        float* a = &red[0][(lane + 32 * i) * 4];
+        float* b = &red[1][(lane + 32 * i) * 4];
+        a[0] += dg_acc[i].x; a[1] += dg_acc[i].y; a[2] += dg_acc[i].z; a[3] += dg_acc[i].w;
+        b[0] += db_acc[i].x; b[1] += db_acc[i].y; b[2] += db_acc[i].z; b[3] += db_acc[i].w;
+      }
+    }
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < W; c += blockDim.x) {
+    atomicAdd(dgamma + c, red[0][c]);
+    atomicAdd(dbeta + c, red[1][c]);
   }
 }
 
@@ -162,70 +175,72 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
 // qkv bf16 [rows,3W], o bf16 [rows,W] (forward output), dout fp32 [rows,W] -> dqkv bf16 [rows,3W].
 //   P = softmax(scale Q K^T + causal), D_i = sum_d dO_id O_id, dP = dO V^T, dS = P o (dP - D),
 //   dV = P^T dO, dQ = scale dS K, dK = scale dS^T Q.
-constexpr int ATTB_THREADS = 128;
-constexpr int ATTB_SMEM = (4 * 77 * 65 + 2 * 77 * 78 + 77) * 4;
+constexpr int ATTB_THREADS = 256;
+__host__ __device__ constexpr int attb_smem_bytes(int T) { return (4 * T * 65 + 2 * T * (T + 1) + T) * 4; }
 
+// T = longest sequence of the batch (sizes the shared-memory arrays, so short captions fit several CTAs per SM)
 __global__ void __launch_bounds__(ATTB_THREADS) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                      const __nv_bfloat16* __restrict__ o,
                                                                      const float* __restrict__ dout, const int4* __restrict__ meta,
-                                                                     int W, __nv_bfloat16* __restrict__ dqkv) {
+                                                                     int W, int T, __nv_bfloat16* __restrict__ dqkv) {
   extern __shared__ float sm[];
-  float (*Q)[65] = reinterpret_cast<float (*)[65]>(sm);
-  float (*K)[65] = reinterpret_cast<float (*)[65]>(sm + 77 * 65);
-  float (*V)[65] = reinterpret_cast<float (*)[65]>(sm + 2 * 77 * 65);
-  float (*dO)[65] = reinterpret_cast<float (*)[65]>(sm + 3 * 77 * 65);
-  float (*P)[78] = reinterpret_cast<float (*)[78]>(sm + 4 * 77 * 65);
-  float (*dS)[78] = reinterpret_cast<float (*)[78]>(sm + 4 * 77 * 65 + 77 * 78);
-  float* Dv = sm + 4 * 77 * 65 + 2 * 77 * 78;
+  float* Q = sm;
+  float* K = Q + T * 65;
+  float* V = K + T * 65;
+  float* dO = V + T * 65;
+  float* P = dO + T * 65;
+  float* dS = P + T * (T + 1);
+  float* Dv = dS + T * (T + 1);
+  const int TP = T + 1;
   const int seq = blockIdx.x, head = blockIdx.y;
   const int4 mt = meta[seq];
-  const int row0 = mt.x, t = mt.y;                     // training batches are packed without prefix sharing (p = 0)
+  const int row0 = mt.x, t = min(mt.y, T);             // training batches are packed without prefix sharing (p = 0)
   const size_t ld = static_cast<size_t>(3) * W;
   for (int idx = threadIdx.x; idx < t * 64; idx += blockDim.x) {
     const int r = idx >> 6, d = idx & 63;
     const __nv_bfloat16* b = qkv + static_cast<size_t>(row0 + r) * ld + head * 64 + d;
-    Q[r][d] = __bfloat162float(b[0]);
-    K[r][d] = __bfloat162float(b[W]);
-    V[r][d] = __bfloat162float(b[2 * W]);
-    dO[r][d] = dout[static_cast<size_t>(row0 + r) * W + head * 64 + d];
+    Q[r * 65 + d] = __bfloat162float(b[0]);
+    K[r * 65 + d] = __bfloat162float(b[W]);
+    V[r * 65 + d] = __bfloat162float(b[2 * W]);
+    dO[r * 65 + d] = dout[static_cast<size_t>(row0 + r) * W + head * 64 + d];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < t; i += blockDim.x) {  // D_i
     float s = 0.f;
-    for (int d = 0; d < 64; ++d) s += dO[i][d] * __bfloat162float(o[static_cast<size_t>(row0 + i) * W + head * 64 + d]);
+    for (int d = 0; d < 64; ++d) s += dO[i * 65 + d] * __bfloat162float(o[static_cast<size_t>(row0 + i) * W + head * 64 + d]);
     Dv[i] = s;
   }
   for (int idx = threadIdx.x; idx < t * t; idx += blockDim.x) {   // scores and dP
     const int i = idx / t, j = idx - i * t;
     float s = 0.f, dp = 0.f;
     if (j <= i) {
-      for (int d = 0; d < 64; ++d) { s += Q[i][d] * K[j][d]; dp += dO[i][d] * V[j][d]; }
+      for (int d = 0; d < 64; ++d) { s += Q[i * 65 + d] * K[j * 65 + d]; dp += dO[i * 65 + d] * V[j * 65 + d]; }
       s *= 0.125f;
     } else {
       s = -INFINITY;
     }
-    P[i][j] = s;
-    dS[i][j] = dp;
+    P[i * TP + j] = s;
+    dS[i * TP + j] = dp;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < t; i += blockDim.x) {  // row softmax, then dS
     float m = -INFINITY;
-    for (int j = 0; j <= i; ++j) m = fmaxf(m, P[i][j]);
+    for (int j = 0; j <= i; ++j) m = fmaxf(m, P[i * TP + j]);
     float l = 0.f;
-    for (int j = 0; j <= i; ++j) { const float e = expf(P[i][j] - m); P[i][j] = e; l += e; }
+    for (int j = 0; j <= i; ++j) { const float e = expf(P[i * TP + j] - m); P[i * TP + j] = e; l += e; }
     const float inv = 1.f / l, di = Dv[i];
     for (int j = 0; j < t; ++j) {
-      const float pj = j <= i ? P[i][j] * inv : 0.f;
-      P[i][j] = pj;
-      dS[i][j] = pj * (dS[i][j] - di);
+      const float pj = j <= i ? P[i * TP + j] * inv : 0.f;
+      P[i * TP + j] = pj;
+      dS[i * TP + j] = pj * (dS[i * TP + j] - di);
     }
   }
   __syncthreads();
   for (int idx = threadIdx.x; idx < t * 64; idx += blockDim.x) {
     const int r = idx >> 6, d = idx & 63;
     float dq = 0.f, dk = 0.f, dv = 0.f;
-    for (int j = 0; j <= r; ++j) dq += dS[r][j] * K[j][d];
-    for (int i = r; i < t; ++i) { dk += dS[i][r] * Q[i][d]; dv += P[i][r] * dO[i][d]; }
+    for (int j = 0; j <= r; ++j) dq += dS[r * TP + j] * K[j * 65 + d];
+    for (int i = r; i < t; ++i) { dk += dS[i * TP + r] * Q[i * 65 + d]; dv += P[i * TP + r] * dO[i * 65 + d]; }
     __nv_bfloat16* b = dqkv + static_cast<size_t>(row0 + r) * ld + head * 64 + d;
     b[0] = __float2bfloat16_rn(dq * 0.125f);
     b[W] = __float2bfloat16_rn(dk * 0.125f);
