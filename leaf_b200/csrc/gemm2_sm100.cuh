@@ -36,6 +36,11 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -120,29 +125,37 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
 
+  // The producer and the MMA issuer run as WHOLE warps with warp-uniform state and elect one lane only for the
+  // asynchronous instructions themselves. Written as `if (lane == 0) { loop }` the same code compiled to ~130
+  // dependent SASS instructions per k-block (ELECT + R2UR per descriptor word), which at ~5 cycles each is MORE than
+  // the 512 tensor-pipe cycles of the 4 MMAs it issues: the issuing thread, not TMA or the epilogue, capped the
+  // tensor pipe at 63-81 % (ncu source page, profiles/r6).
   if (warp == WARP_TMA) {
     // ===== TMA producer (both CTAs) =====
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-        const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    const int a_row_off = static_cast<int>(rank) * 128;
+    for (int tile = pair; tile < total_tiles; tile += n_pairs) {
+      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int a_row = m_blk * GEMM2_BM + a_row_off, b_row = n_blk * GEMM_BN + a_row_off;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
           const uint32_t sa = smem_base + stage * GEMM2_STAGE_BYTES;
-          const uint32_t sb = sa + GEMM2_A_BYTES;
           const uint32_t fb = full_bar(stage) & PEER_BIT_MASK;
           if (leader) mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
-          tma_load_2d_2sm(sa, &tmap_a, fb, kb * GEMM_BK, m_blk * GEMM2_BM + static_cast<int>(rank) * 128);
-          tma_load_2d_2sm(sb, &tmap_b, fb, kb * GEMM_BK, n_blk * GEMM_BN + static_cast<int>(rank) * 128);
-          if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
+          tma_load_2d_2sm(sa, &tmap_a, fb, kb * GEMM_BK, a_row);
+          tma_load_2d_2sm(sa + GEMM2_A_BYTES, &tmap_b, fb, kb * GEMM_BK, b_row);
         }
+        __syncwarp();
+        if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == WARP_MMA) {
-    // ===== MMA issuer: one thread of the leader CTA =====
-    if (leader && lane == 0) {
+    // ===== MMA issuer: the leader CTA's warp, one elected lane issues =====
+    if (leader) {
       constexpr uint32_t idesc = make_idesc_bf16(GEMM2_BM, GEMM_BN);
+      const uint64_t desc0 = make_smem_desc_sw128(smem_base);           // stage 0, A; +2/k-step, +stage bytes >> 4 per stage
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -154,16 +167,17 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * GEMM2_STAGE_BYTES;
-          const uint32_t sb = sa + GEMM2_A_BYTES;
-          const uint64_t adesc = make_smem_desc_sw128(sa);
-          const uint64_t bdesc = make_smem_desc_sw128(sb);
-#pragma unroll
-          for (int k = 0; k < GEMM_BK / GEMM_UMMA_K; ++k)
-            umma_bf16_2sm(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                          (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(empty_bar(stage));
-          if (kb == k_blocks - 1) umma_commit_2sm(tfull_bar(acc));
+          if (elect_one()) {
+            const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * (GEMM2_STAGE_BYTES >> 4));
+            const uint64_t bdesc = adesc + static_cast<uint64_t>(GEMM2_A_BYTES >> 4);
+            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            umma_bf16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
+            umma_bf16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            umma_commit_2sm(empty_bar(stage));
+            if (kb == k_blocks - 1) umma_commit_2sm(tfull_bar(acc));
+          }
+          __syncwarp();
           if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
