@@ -121,9 +121,12 @@ int leaf_expand_tokenize(leaf_handle_t h, const uint8_t* caps, const int32_t* ca
  * base [N] (may be NULL): base[i] = j >= 0 names another row of this batch (with base[j] = -1) that row i was
  * derived from; positions where both token rows agree have identical hidden states under the causal mask, so
  * they are computed once (on row j) and row i's attention reads row j's keys/values for them. Results are
- * bit-identical to base == NULL. */
+ * bit-identical to base == NULL.
+ * dedup_group > 1: rows [0, dedup_rows) come in groups of dedup_group consecutive rows (the n candidates of a sample);
+ * a row whose tokens equal an EARLIER row of its group is not encoded again - it receives that row's features (bit
+ * identical, so exact ties keep resolving to the first index). dedup_group <= 1 disables it. */
 int leaf_encode(leaf_handle_t h, const int32_t* tok, const int32_t* len, const int32_t* base, int32_t N,
-                int32_t normalize, float* feat_out, void* stream);
+                int32_t dedup_rows, int32_t dedup_group, int32_t normalize, float* feat_out, void* stream);
 
 /* ---- K3: TextFARE score + per-sample argmax ----------------------------------------------------
  * Replaces utils_attacks.py:332-348 / :370-386 / :393. feat [B*n,E] fp32, anchor [B,E] fp32.

@@ -97,7 +97,7 @@ struct leaf_engine {
   __nv_bfloat16* h = nullptr;         // [rows_cap, W]  LN output / attention output
   __nv_bfloat16* big = nullptr;       // [rows_cap, 4W] qkv (3W) or MLP hidden (4W)
   __nv_bfloat16* pooled = nullptr;    // [max_seqs, W]
-  int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr;
+  int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr, *dup_of = nullptr;
   int4* meta = nullptr;
   // bookkeeping
   int64_t launches = 0;
@@ -218,9 +218,9 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
 
 static void free_workspace(leaf_engine* e) {
   cudaFree(e->x); cudaFree(e->h); cudaFree(e->big); cudaFree(e->pooled);
-  cudaFree(e->cu); cudaFree(e->eos_row); cudaFree(e->total_rows); cudaFree(e->pfx); cudaFree(e->own_len); cudaFree(e->meta);
+  cudaFree(e->cu); cudaFree(e->eos_row); cudaFree(e->total_rows); cudaFree(e->pfx); cudaFree(e->own_len); cudaFree(e->dup_of); cudaFree(e->meta);
   e->x = nullptr; e->h = nullptr; e->big = nullptr; e->pooled = nullptr;
-  e->cu = e->eos_row = e->total_rows = e->pfx = e->own_len = nullptr;
+  e->cu = e->eos_row = e->total_rows = e->pfx = e->own_len = e->dup_of = nullptr;
   e->meta = nullptr;
   e->max_seqs = 0; e->rows_cap = 0;
   e->tmaps.clear();
@@ -420,6 +420,7 @@ extern "C" int leaf_reserve(leaf_handle_t e, int32_t max_seqs) {
   CK(cudaMalloc(&e->eos_row, static_cast<size_t>(max_seqs) * 4));
   CK(cudaMalloc(&e->pfx, static_cast<size_t>(max_seqs) * 4));
   CK(cudaMalloc(&e->own_len, static_cast<size_t>(max_seqs) * 4));
+  CK(cudaMalloc(&e->dup_of, static_cast<size_t>(max_seqs) * 4));
   CK(cudaMalloc(&e->meta, static_cast<size_t>(max_seqs) * 16));
   CK(cudaMalloc(&e->total_rows, 4));
   CK(cudaMemset(e->total_rows, 0, 4));
@@ -466,7 +467,7 @@ static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev,
 }
 
 extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* len, const int32_t* base, int32_t N,
-                           int32_t normalize, float* feat_out, void* stream) {
+                           int32_t dedup_rows, int32_t dedup_group, int32_t normalize, float* feat_out, void* stream) {
   if (!e || !tok || !len || !feat_out) return fail(LEAF_ERR_INVALID, "null argument");
   if (!e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
   if (N <= 0) return fail(LEAF_ERR_INVALID, "N=%d", N);
@@ -475,9 +476,16 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
   const int W = e->cfg.width, E = e->cfg.embed_dim, H = e->cfg.heads;
   const int rows_max = static_cast<int>(static_cast<long>(N) * LEAF_CTX);
   int rc;
-  prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, base, N, e->pfx, e->own_len);
+  const int* dup = nullptr;
+  if (dedup_group > 1 && dedup_rows > 0) {
+    if (dedup_rows > N || dedup_rows % dedup_group != 0) return fail(LEAF_ERR_INVALID, "dedup_rows=%d dedup_group=%d N=%d", dedup_rows, dedup_group, N);
+    dedup_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, dedup_rows, dedup_group, N, e->dup_of);
+    e->launches++;
+    dup = e->dup_of;
+  }
+  prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, base, dup, N, e->pfx, e->own_len);
   scan_lengths_kernel<<<1, 1024, 0, st>>>(e->own_len, N, e->cu, e->total_rows);
-  meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(e->cu, e->pfx, base, N, e->meta, e->eos_row);
+  meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(e->cu, e->pfx, base, dup, N, e->meta, e->eos_row);
   embed_kernel<<<N, 256, 0, st>>>(tok, e->meta, N, W, e->wp.token_embedding, e->wp.positional_embedding, e->x);
   e->launches += 4;
   CK(cudaGetLastError());
@@ -669,9 +677,9 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
   int rc;
   t.have_forward = false;
   CK(cudaMemcpyAsync(t.tok, tok, static_cast<size_t>(N) * LEAF_CTX * 4, cudaMemcpyDeviceToDevice, st));
-  prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, nullptr, N, t.pfx, t.own_len);
+  prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, nullptr, nullptr, N, t.pfx, t.own_len);
   scan_lengths_kernel<<<1, 1024, 0, st>>>(t.own_len, N, t.cu, t.total_rows, t.total_rows + 1);
-  meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(t.cu, t.pfx, nullptr, N, t.meta, t.eos_row);
+  meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(t.cu, t.pfx, nullptr, nullptr, N, t.meta, t.eos_row);
   e->launches += 3;
   int mt[2] = {0, 0};
   CK(cudaMemcpyAsync(mt, t.total_rows, 8, cudaMemcpyDeviceToHost, st));

@@ -20,7 +20,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// exclusive scan of the row lengths -> cu[N+1]; also clamps len to [1, 77]. Single CTA (N <= ~10^5).
+// exclusive scan of the (own) row lengths -> cu[N+1]; clamps to [0, 77]. Single CTA (N <= ~10^5).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int* __restrict__ len, int N, int* __restrict__ cu,
                                                             int* __restrict__ total_rows, int* __restrict__ max_len = nullptr) {
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int* __restric
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int base = 0; base < N; base += 1024) {
     const int i = base + threadIdx.x;
-    int v = (i < N) ? min(max(len[i], 1), 77) : 0;
+    int v = (i < N) ? min(max(len[i], 0), 77) : 0;      // 0 = duplicate row, encoded with its first occurrence
     if (max_len) atomicMax(&vmax_s, v);
     int inc = v;
 #pragma unroll
@@ -72,12 +72,17 @@ __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int* __restric
 // positions [p, t) of row i are computed and its attention reads the base's keys/values for [0, p).
 // own_len[i] = t - p with p = min(common prefix, t - 1) (the pooled EOS row is always computed). One warp per row.
 // ---------------------------------------------------------------------------------------------
+// dup_of[i] >= 0 (from dedup_kernel): row i has the same tokens as an earlier row and owns NO rows at all.
 __global__ void __launch_bounds__(256) prefix_kernel(const int* __restrict__ tok, const int* __restrict__ len,
-                                                     const int* __restrict__ base, int N, int* __restrict__ pfx,
-                                                     int* __restrict__ own_len) {
+                                                     const int* __restrict__ base, const int* __restrict__ dup_of, int N,
+                                                     int* __restrict__ pfx, int* __restrict__ own_len) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N) return;
   const int t = min(max(len[i], 1), 77);
+  if (dup_of && dup_of[i] >= 0) {
+    if (lane == 0) { pfx[i] = t; own_len[i] = 0; }
+    return;
+  }
   int p = 0;
   const int b = base ? base[i] : -1;
   if (b >= 0 && b < N && b != i) {
@@ -95,15 +100,36 @@ __global__ void __launch_bounds__(256) prefix_kernel(const int* __restrict__ tok
   if (lane == 0) { pfx[i] = p; own_len[i] = t - p; }
 }
 
-// meta[i] = {own_row, t, p, base_row}; eos_row[i] = last own row
-__global__ void meta_kernel(const int* __restrict__ cu, const int* __restrict__ pfx, const int* __restrict__ base, int N,
-                            int4* __restrict__ meta, int* __restrict__ eos_row) {
+// Duplicate candidates inside a sample (e.g. 'a' and 'A' written at the same position: the tokenizer lower-cases, so
+// ~14 % of the phase-2 rows repeat an earlier row) are encoded once: dup_of[i] = first earlier row of the same group of
+// `group` consecutive rows with identical length and tokens, else -1. One warp per row; rows >= n_rows are never grouped.
+__global__ void __launch_bounds__(256) dedup_kernel(const int* __restrict__ tok, const int* __restrict__ len, int n_rows,
+                                                    int group, int N, int* __restrict__ dup_of) {
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= N) return;
+  int found = -1;
+  if (i < n_rows) {
+    const int t = len[i];
+    const int a0 = tok[i * 77 + lane], a1 = tok[i * 77 + 32 + lane], a2 = lane < 13 ? tok[i * 77 + 64 + lane] : 0;
+    for (int j = (i / group) * group; j < i; ++j) {
+      if (len[j] != t) continue;                                          // warp-uniform
+      const bool same = a0 == tok[j * 77 + lane] && a1 == tok[j * 77 + 32 + lane] && (lane >= 13 || a2 == tok[j * 77 + 64 + lane]);
+      if (__all_sync(0xffffffffu, same)) { found = j; break; }
+    }
+  }
+  if (lane == 0) dup_of[i] = found;
+}
+
+// meta[i] = {own_row, t, p, base_row}; eos_row[i] = last own row (of the first occurrence for a duplicate)
+__global__ void meta_kernel(const int* __restrict__ cu, const int* __restrict__ pfx, const int* __restrict__ base,
+                            const int* __restrict__ dup_of, int N, int4* __restrict__ meta, int* __restrict__ eos_row) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int own = cu[i], n_own = cu[i + 1] - own, p = pfx[i];
-  const int b = (base && p > 0) ? base[i] : i;
+  const int b = (base && p > 0 && base[i] >= 0) ? base[i] : i;
   meta[i] = make_int4(own, p + n_own, p, cu[b]);
-  eos_row[i] = own + n_own - 1;
+  const int d = (dup_of && dup_of[i] >= 0) ? dup_of[i] : i;
+  eos_row[i] = cu[d + 1] - 1;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -110,6 +110,15 @@ def test_shared_prefix_is_bit_identical():
     rows_plain = eng.last_rows()
     assert torch.equal(shared, plain)
     assert rows_plain == int(ln.sum()) and rows_shared < 0.75 * rows_plain
+    # duplicate elimination inside a sample: 'a' / 'A' at the same position tokenize identically
+    chr_[:, 1::2] = np.where(chr_[:, 0::2] > 96, chr_[:, 0::2] - 32, chr_[:, 0::2])      # upper-case twins of the even columns
+    pos[:, 1::2] = pos[:, 0::2]
+    tok, ln, base = eng.expand_tokenize(d, o, B, n, torch.from_numpy(pos).cuda(), torch.from_numpy(chr_).cuda())
+    ded = eng.encode_tokens(tok, ln, False, base, (B * n, n))
+    rows_ded = eng.last_rows()
+    ref = eng.encode_tokens(tok, ln, False, None)
+    assert torch.equal(ded, ref)
+    assert rows_ded < 0.8 * eng.encode_tokens(tok, ln, False, base).shape[0] * 77 and rows_ded < rows_shared
 
 
 def _golden_attack(golden_dir):
@@ -214,7 +223,7 @@ def test_full_size_properties_vit_h():
     d, o = eng.upload_captions(caps)
     tok, ln, base = eng.expand_tokenize(d, o, B, n, torch.from_numpy(pos).cuda(), torch.from_numpy(chr_).cuda())
     assert torch.equal(tok.view(-1, 77)[:B * n].view(B, n, 77)[:, 7], tok[:B * n].view(B, n, 77)[:, 3])
-    shared = eng.encode_tokens(tok, ln, False, base)
+    shared = eng.encode_tokens(tok, ln, False, base, (B * n, n))       # shared prefixes + in-sample duplicates
     rows_shared = eng.last_rows()
     plain = eng.encode_tokens(tok, ln, False, None)
     assert eng.last_rows() == int(ln.sum()) and rows_shared < eng.last_rows()
