@@ -303,6 +303,7 @@ def run_ours(a):
     device_step(*all_draws[-1], record=rec)
     torch.cuda.synchronize()
     gemm_ms, gemm_launches = eng.gemm_time_ms()
+    insitu = {name: round(eng.class_time_ms(i)[0], 3) for i, name in enumerate(("gemm", "layernorm", "attention", "pack_embed"))}
     eng.set_timing(False)
     lens = torch.cat([r[0] for r in rec]).double().cpu().numpy()
     rows_exec = sum(r[1] for r in rec)                                        # packed rows the GEMMs really processed
@@ -322,6 +323,7 @@ def run_ours(a):
     roofline = dict(bound="tensor", achieved=achieved, peak=peak_tf, unit="TFLOP/s", frac=achieved / peak_tf, traffic=traffic,
                     kernel="gemm2_bf16_tn_kernel (tcgen05.mma.cta_group::2, all four Linear layers + projection)", peak_source=peak_src, gemm_launches_per_step=gemm_launches,
                     gemm_ms_per_step=gemm_ms, gemm_share_of_step=gemm_ms / step_ms if step_ms else None,
+                    in_situ_ms_per_step=insitu,
                     algorithmic_tflop_per_step=alg_flops / 1e12, executed_gemm_tflop_per_step=gemm_flops / 1e12,
                     credited_gemm_tflops=gemm_flops_credit / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
                     rows_executed_per_step=int(rows_exec), rows_without_prefix_sharing=int(lens.sum()),

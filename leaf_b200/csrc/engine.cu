@@ -102,7 +102,10 @@ struct leaf_engine {
   // bookkeeping
   int64_t launches = 0;
   bool timing = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+  struct Span { cudaEvent_t a, b; int cat; };
+  std::vector<Span> spans;            // cat: 0 GEMM, 1 LayerNorm, 2 attention, 3 everything else of the encode
+  double span_ms[4] = {0, 0, 0, 0};
+  int span_n[4] = {0, 0, 0, 0};
   std::vector<cudaEvent_t> event_pool;
   std::map<std::tuple<const void*, long, long, int>, CUtensorMap> tmaps;
 };
@@ -138,6 +141,17 @@ static cudaEvent_t get_event(leaf_engine* e) {
   return ev;
 }
 
+// CUDA events on the launching stream around a group of launches (only while leaf_set_timing is on)
+struct TimedSpan {
+  leaf_engine* e; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr; int cat;
+  TimedSpan(leaf_engine* e_, int cat_, cudaStream_t st_) : e(e_), st(st_), cat(cat_) {
+    if (e->timing) { a = get_event(e); b = get_event(e); cudaEventRecord(a, st); }
+  }
+  ~TimedSpan() {
+    if (a) { cudaEventRecord(b, st); e->spans.push_back({a, b, cat}); }
+  }
+};
+
 // C[M,N] = A[M,K] . Bt[N,K]^T with the fused epilogue `epi`
 static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, const __nv_bfloat16* Bt, const float* bias,
                        void* C, int ldc, int M, int N, int K, int epi, int act, const int* m_dev, cudaStream_t st) {
@@ -155,8 +169,7 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act;
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
   const long tiles = static_cast<long>(m_tiles) * n_tiles;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (e->timing) { e0 = get_event(e); e1 = get_event(e); cudaEventRecord(e0, st); }
+  TimedSpan span(e, 0, st);
   const int pairs_max = e->sm_count / 2;
   const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
   cudaLaunchConfig_t cfg{};
@@ -176,7 +189,6 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
     case EPI_F32: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32>, ta, tb, p)); break;
     default: return fail(LEAF_ERR_INVALID, "unknown epilogue %d", epi);
   }
-  if (e->timing) { cudaEventRecord(e1, st); e->gemm_events.emplace_back(e0, e1); }
   e->launches++;
   CK(cudaGetLastError());
   return LEAF_OK;
@@ -247,7 +259,7 @@ extern "C" int leaf_destroy(leaf_handle_t e) {
   e->tw = TrainWs();
   free_weights(e);
   for (void* p : e->table_allocs) cudaFree(p);
-  for (auto& pr : e->gemm_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+  for (auto& sp : e->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
   delete e;
   return LEAF_OK;
@@ -449,6 +461,7 @@ static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev,
                             const float* g, const float* b, __nv_bfloat16* y, cudaStream_t st) {
   const int W = e->cfg.width;
   const int vpl = W / 128;
+  TimedSpan span(e, 1, st);
   long warps = rows_max;
   int blocks = static_cast<int>((warps + 7) / 8);
   const int cap = e->sm_count * 8;
@@ -477,6 +490,8 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
   const int rows_max = static_cast<int>(static_cast<long>(N) * LEAF_CTX);
   int rc;
   const int* dup = nullptr;
+  {
+  TimedSpan span(e, 3, st);
   if (dedup_group > 1 && dedup_rows > 0) {
     if (dedup_rows > N || dedup_rows % dedup_group != 0) return fail(LEAF_ERR_INVALID, "dedup_rows=%d dedup_group=%d N=%d", dedup_rows, dedup_group, N);
     dedup_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, dedup_rows, dedup_group, N, e->dup_of);
@@ -488,13 +503,17 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
   meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(e->cu, e->pfx, base, dup, N, e->meta, e->eos_row);
   embed_kernel<<<N, 256, 0, st>>>(tok, e->meta, N, W, e->wp.token_embedding, e->wp.positional_embedding, e->x);
   e->launches += 4;
+  }
   CK(cudaGetLastError());
   for (int l = 0; l < e->cfg.layers; ++l) {
     const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
     const LayerW& w = e->lw[l];
     if ((rc = launch_layernorm(e, e->x, e->total_rows, rows_max, nullptr, p.ln1_w, p.ln1_b, e->h, st))) return rc;
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.qkv_w, w.qkv_b, e->big, 3 * W, rows_max, 3 * W, W, EPI_BF16, 0, e->total_rows, st))) return rc;
-    attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(e->big, e->meta, N, H, W, e->h);
+    {
+      TimedSpan span(e, 2, st);
+      attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(e->big, e->meta, N, H, W, e->h);
+    }
     e->launches++;
     CK(cudaGetLastError());
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.out_w, p.out_b, e->x, W, rows_max, W, W, EPI_F32_RESIDUAL, 0, e->total_rows, st))) return rc;
@@ -563,26 +582,32 @@ extern "C" int64_t leaf_last_rows(leaf_handle_t e) {
   return v;
 }
 
+extern "C" double leaf_timing_ms(leaf_handle_t e, int32_t which, int32_t* launches);
 extern "C" int leaf_set_timing(leaf_handle_t e, int32_t on) {
   if (!e) return fail(LEAF_ERR_INVALID, "null handle");
   e->timing = on != 0;
+  if (e->timing) {                               // a new measurement starts from zero
+    int32_t dummy;
+    leaf_timing_ms(e, 0, &dummy);
+    for (int i = 0; i < 4; ++i) { e->span_ms[i] = 0; e->span_n[i] = 0; }
+  }
   return LEAF_OK;
 }
 
 extern "C" double leaf_timing_ms(leaf_handle_t e, int32_t which, int32_t* launches) {
-  if (!e || which != 0) return 0.0;
-  double total = 0.0;
-  int cnt = 0;
-  for (auto& pr : e->gemm_events) {
-    cudaEventSynchronize(pr.second);
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) { total += ms; ++cnt; }
-    e->event_pool.push_back(pr.first);
-    e->event_pool.push_back(pr.second);
+  if (!e || which < 0 || which > 3) return 0.0;
+  if (!e->spans.empty()) {                       // fold the recorded spans into the per-category totals
+    for (auto& sp : e->spans) {
+      cudaEventSynchronize(sp.b);
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { e->span_ms[sp.cat] += ms; e->span_n[sp.cat]++; }
+      e->event_pool.push_back(sp.a);
+      e->event_pool.push_back(sp.b);
+    }
+    e->spans.clear();
   }
-  e->gemm_events.clear();
-  if (launches) *launches = cnt;
-  return total;
+  if (launches) *launches = e->span_n[which];
+  return e->span_ms[which];
 }
 
 // =====================================================================================================================

@@ -299,8 +299,13 @@ class LeafEngine:
         check(self._lib.leaf_set_timing(self._h, 1 if on else 0))
 
     def gemm_time_ms(self):
+        return self.class_time_ms(0)
+
+    def class_time_ms(self, which: int):
+        """(ms, launches) of kernel class `which` (0 GEMM, 1 LayerNorm, 2 attention, 3 packing + embedding) since
+        set_timing(True): CUDA events on the launching stream around every launch of the class."""
         n = ctypes.c_int32(0)
-        ms = self._lib.leaf_timing_ms(self._h, 0, ctypes.byref(n))
+        ms = self._lib.leaf_timing_ms(self._h, int(which), ctypes.byref(n))
         return float(ms), int(n.value)
 
     def last_rows(self) -> int:

@@ -318,3 +318,82 @@ def attack_text_leaf_oracle(encode, tokenizer, sentences, anchor_features, objec
     best = torch.take_along_dim(feats, ids_best.view(-1, 1, 1).repeat(1, 1, feats.shape[-1]),
                                 dim=1).squeeze(1)                                   # :393
     return best, sentences
+
+
+# ----------------------------------------------------------------------------------------------
+# single-sentence evaluation attacks
+# ----------------------------------------------------------------------------------------------
+def all_sentences(S: str, V, subset_z=None) -> list:
+    """generate_all_sentences(S, V, subset_z, k=1, alternative=-1) (utils_attacks.py:275-295): for every position z of
+    subset_z (default: all 2*len(S)+1), every character of V."""
+    if subset_z is None:
+        subset_z = range(2 * len(S) + 1)
+    return [edit_sentence(S, int(z), V[u]) for z in subset_z for u in range(len(V))]
+
+
+def _batched_loss(encode, tokenizer, SS, anchor, objective, batch_size, encode_2=None, anchor_2=None):
+    """The reference's batching loop (utils_attacks.py:420-445, :483-517, :538-573) INCLUDING its off-by-one:
+    `end = min((i+1)*bs, len-1)` never evaluates the LAST candidate. Returns loss[len-1]."""
+    tokens = tokenizer(SS)
+    norm = objective in ("sim", "dissim")
+    out = []
+    for i in range(len(tokens) // batch_size + 1):
+        beg, end = i * batch_size, min((i + 1) * batch_size, len(tokens) - 1)
+        if beg >= end:
+            continue
+        f = encode(tokens[beg:end], norm).view(end - beg, -1)
+        l = score(f.unsqueeze(0), anchor.view(1, -1), objective).squeeze(0)
+        if encode_2 is not None:
+            f2 = encode_2(tokens[beg:end], norm).view(end - beg, -1)
+            l = (l + score(f2.unsqueeze(0), anchor_2.view(1, -1), objective).squeeze(0)) / 2
+        out.append(l)
+    return torch.cat(out, dim=0)
+
+
+def attack_text_charmer_oracle(encode, tokenizer, sentence, anchor_features, objective="l2", n=10, k=1, V=V_DEFAULT,
+                               valid_fn=None, batch_size=20 * 128, encode_2=None, anchor_2=None, trace=None):
+    """attack_text_charmer_inference (utils_attacks.py:451-580): per round, probe every position with a space, keep the
+    top-n positions (torch.topk), then try every character of V at those positions and keep the argmax.
+    Deviation noted in DESIGN.md: with model_2 and objective 'l2' the reference's first phase raises (a misplaced `/2`
+    on list.append's None, :496); here every objective averages the two losses, which is what :498-513 do."""
+    anchor = anchor_features
+    if objective in ("dissim", "sim"):
+        anchor = anchor / anchor.norm(dim=-1, keepdim=True)
+        if anchor_2 is not None:
+            anchor_2 = anchor_2 / anchor_2.norm(dim=-1, keepdim=True)
+    dist = 0
+    for dist in range(k):
+        SS = all_sentences(sentence, [ord(" ")])                                   # :476-477
+        if valid_fn is not None:                                                   # :478-481
+            valid = valid_fn([sentence], [SS])[0]
+            SS = [s if v else sentence for s, v in zip(SS, valid)]
+        loss = _batched_loss(encode, tokenizer, SS, anchor, objective, batch_size, encode_2, anchor_2)
+        top = torch.topk(loss, min(n, loss.shape[0]), dim=0).indices               # :519
+        SS = all_sentences(sentence, V, subset_z=[int(z) for z in top])            # :524
+        if valid_fn is not None:                                                   # :532-537
+            valid = valid_fn([sentence], [SS])[0]
+            SS = [s if v else sentence for s, v in zip(SS, valid)]
+        loss2 = _batched_loss(encode, tokenizer, SS, anchor, objective, batch_size, encode_2, anchor_2)
+        if trace is not None:
+            trace.setdefault("rounds", []).append(dict(sentence=sentence, loss1=loss.clone(), top=top.clone(), loss2=loss2.clone()))
+        sentence = SS[int(torch.argmax(loss2))]                                    # :575
+    return sentence, dist + 1
+
+
+def attack_text_bruteforce_oracle(encode, tokenizer, sentence, anchor_features, objective="l2", V=V_DEFAULT,
+                                  valid_fn=None, batch_size=20 * 128, trace=None):
+    """attack_text_bruteforce (utils_attacks.py:395-449): every position x every character, k = 1; objectives 'l2' and
+    'dissim' only (anything else leaves the loss undefined there and raises)."""
+    if objective not in ("l2", "dissim"):
+        raise ValueError(objective)
+    anchor = anchor_features
+    if objective == "dissim":
+        anchor = anchor / anchor.norm(dim=-1, keepdim=True)
+    SS = all_sentences(sentence, V)                                                # :412
+    if valid_fn is not None:                                                       # :415-418
+        valid = valid_fn([sentence], [SS])[0]
+        SS = [s if v else sentence for s, v in zip(SS, valid)]
+    loss = _batched_loss(encode, tokenizer, SS, anchor, objective, batch_size)
+    if trace is not None:
+        trace["loss"] = loss.clone()
+    return SS[int(torch.argmax(loss))], 1

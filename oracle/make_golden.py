@@ -168,6 +168,46 @@ def gen_attack():
     print("attack cases", len(cases))
 
 
+def gen_eval_attacks():
+    """attack_text_charmer_inference / attack_text_bruteforce (utils_attacks.py:395-580), one sentence at a time."""
+    tok = open_clip.get_tokenizer("ViT-L-14")
+    cfg = synth.TOWERS["tiny"]
+    sd = synth.random_tower_state_dict(cfg, seed=31, exact_numpy=True)
+    sd_frozen = synth.perturbed_copy(sd, seed=32, std=1e-2, exact_numpy=True)
+    sd2 = synth.random_tower_state_dict(cfg, seed=33, exact_numpy=True)
+    model, frozen, model2 = build_ref_clip(cfg, sd), build_ref_clip(cfg, sd_frozen), build_ref_clip(cfg, sd2)
+    charmer, brute, arrays = [], [], {}
+    caps = synth.make_captions(3, seed=200, kind="typical") + synth.make_captions(2, seed=201, kind="short") + ["a cat's toy & a dog", "ab"]
+    for ci, (si, n, k, objective, bs, two) in enumerate([
+            (0, 10, 1, "l2", 2560, False), (1, 5, 2, "l2", 64, False), (2, 10, 1, "negl2", 2560, False),
+            (3, 20, 3, "l2", 2560, False), (4, 3, 1, "sim", 2560, False), (5, 10, 1, "dissim", 100, False),
+            (6, 10, 1, "l2", 2560, False), (0, 6, 1, "dissim", 2560, True), (5, 4, 2, "sim", 2560, True)]):
+        S = caps[si]
+        norm = objective in ("sim", "dissim")
+        with torch.no_grad():
+            anchor = frozen.encode_text(tok([S]), normalize=norm)
+            anchor2 = model2.encode_text(tok(["another " + S]), normalize=norm) if two else None
+            adv, dist = utils_attacks.attack_text_charmer_inference(
+                model, tok, S, anchor.clone(), "cpu", objective=objective, n=n, k=k, V=V, constrain=False, batch_size=bs,
+                model_2=model2 if two else None, model_2_anchor_features=anchor2.clone() if two else None)
+        charmer.append(dict(sentence=S, n=n, k=k, objective=objective, batch_size=bs, two=two, adv=adv, dist=dist))
+        arrays[f"charmer_anchor_{ci}"] = anchor.numpy()
+        if two:
+            arrays[f"charmer_anchor2_{ci}"] = anchor2.numpy()
+    for ci, (si, objective, bs) in enumerate([(3, "l2", 2560), (4, "dissim", 500), (6, "l2", 64), (1, "l2", 2560)]):
+        S = caps[si]
+        with torch.no_grad():
+            anchor = frozen.encode_text(tok([S]), normalize=objective == "dissim")
+            adv, dist = utils_attacks.attack_text_bruteforce(model, tok, S, anchor.clone(), "cpu", batch_size=bs,
+                                                             objective=objective, V=V, constrain=False)
+        brute.append(dict(sentence=S, objective=objective, batch_size=bs, adv=adv, dist=dist))
+        arrays[f"brute_anchor_{ci}"] = anchor.numpy()
+    json.dump({"tower": "tiny", "seed": 31, "seed2": 33, "charmer": charmer, "bruteforce": brute},
+              open(os.path.join(OUT, "eval_attack_golden.json"), "w"))
+    np.savez_compressed(os.path.join(OUT, "eval_attack_golden.npz"), **arrays)
+    print("charmer cases", len(charmer), "bruteforce cases", len(brute))
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -175,3 +215,4 @@ if __name__ == "__main__":
     gen_tokenizer()
     gen_tower()
     gen_attack()
+    gen_eval_attacks()
