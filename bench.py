@@ -304,6 +304,10 @@ def run_ours(a):
     torch.cuda.synchronize()
     gemm_ms, gemm_launches = eng.gemm_time_ms()
     insitu = {name: round(eng.class_time_ms(i)[0], 3) for i, name in enumerate(("gemm", "layernorm", "attention", "pack_embed"))}
+    for epi, name in enumerate(("gemm_qkv_bf16", "gemm_fc1_bf16_act", "gemm_out_fc2_residual", "gemm_proj_f32")):
+        ms_epi, n_epi = eng.class_time_ms(4 + epi)
+        if n_epi:
+            insitu[name] = [round(ms_epi, 3), n_epi]
     eng.set_timing(False)
     lens = torch.cat([r[0] for r in rec]).double().cpu().numpy()
     rows_exec = sum(r[1] for r in rec)                                        # packed rows the GEMMs really processed

@@ -165,7 +165,7 @@ int64_t leaf_launch_count(leaf_handle_t h, int32_t reset);
 /* Packed-row count (sum of len) of the last leaf_encode; synchronises the device. */
 int64_t leaf_last_rows(leaf_handle_t h);
 /* Accumulated device time (ms) of the launches of class `which` (0 = GEMM, 1 = LayerNorm, 2 = attention, 3 = row
- * packing + embedding) between CUDA events recorded on the launching stream, since timing was last enabled with
+ * packing + embedding, 4 + e = the GEMM launches with epilogue e) between CUDA events recorded on the launching stream, since timing was last enabled with
  * leaf_set_timing(h, 1). Synchronises on the recorded events. */
 int leaf_set_timing(leaf_handle_t h, int32_t on);
 double leaf_timing_ms(leaf_handle_t h, int32_t which, int32_t* launches);

@@ -104,8 +104,8 @@ struct leaf_engine {
   bool timing = false;
   struct Span { cudaEvent_t a, b; int cat; };
   std::vector<Span> spans;            // cat: 0 GEMM, 1 LayerNorm, 2 attention, 3 everything else of the encode
-  double span_ms[4] = {0, 0, 0, 0};
-  int span_n[4] = {0, 0, 0, 0};
+  double span_ms[8] = {0};         // 4 + epi: the GEMM launches of one epilogue kind (also counted in class 0)
+  int span_n[8] = {0};
   std::vector<cudaEvent_t> event_pool;
   std::map<std::tuple<const void*, long, long, int>, CUtensorMap> tmaps;
 };
@@ -169,7 +169,7 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act;
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
   const long tiles = static_cast<long>(m_tiles) * n_tiles;
-  TimedSpan span(e, 0, st);
+  TimedSpan span(e, 4 + epi, st);
   const int pairs_max = e->sm_count / 2;
   const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
   cudaLaunchConfig_t cfg{};
@@ -589,18 +589,21 @@ extern "C" int leaf_set_timing(leaf_handle_t e, int32_t on) {
   if (e->timing) {                               // a new measurement starts from zero
     int32_t dummy;
     leaf_timing_ms(e, 0, &dummy);
-    for (int i = 0; i < 4; ++i) { e->span_ms[i] = 0; e->span_n[i] = 0; }
+    for (int i = 0; i < 8; ++i) { e->span_ms[i] = 0; e->span_n[i] = 0; }
   }
   return LEAF_OK;
 }
 
 extern "C" double leaf_timing_ms(leaf_handle_t e, int32_t which, int32_t* launches) {
-  if (!e || which < 0 || which > 3) return 0.0;
+  if (!e || which < 0 || which > 7) return 0.0;
   if (!e->spans.empty()) {                       // fold the recorded spans into the per-category totals
     for (auto& sp : e->spans) {
       cudaEventSynchronize(sp.b);
       float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) { e->span_ms[sp.cat] += ms; e->span_n[sp.cat]++; }
+      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+        e->span_ms[sp.cat] += ms; e->span_n[sp.cat]++;
+        if (sp.cat >= 4) { e->span_ms[0] += ms; e->span_n[0]++; }
+      }
       e->event_pool.push_back(sp.a);
       e->event_pool.push_back(sp.b);
     }
