@@ -135,6 +135,14 @@ int leaf_encode(leaf_handle_t h, const int32_t* tok, const int32_t* len, const i
 int leaf_score(leaf_handle_t h, const float* feat, const float* anchor, int32_t B, int32_t n, int32_t objective,
                float* loss_out, int32_t* best_out, float* best_feat_out, void* stream);
 
+/* Top-k of a score vector, for the single-sentence evaluation attacks built on K1-K3 (attack_text_charmer_inference,
+ * utils_attacks.py:451-580: torch.topk of the position scores :519 and torch.argmax over the whole candidate list
+ * :575; attack_text_bruteforce :447). score_a [m] fp32; score_b (may be NULL) a second tower's scores of the same
+ * candidates, averaged as (a+b)/2 (:498-513). idx_out [k] int32, val_out [k] (may be NULL): value descending, ties by
+ * ascending index (k = 1 is torch.argmax's first-index rule). */
+int leaf_topk(leaf_handle_t h, const float* score_a, const float* score_b, int32_t m, int32_t k, int32_t* idx_out,
+              float* val_out, void* stream);
+
 /* ---- K4: train-mode forward + backward of the selected adversarial batch -----------------------
  * Replaces model.encode_text(adv_tokens) under autograd and loss.backward() of utils_AT.py:317-337 (the loss itself,
  * mse(...).sum(-1).mean() on [B,E], stays a two-line torch expression on top of feat_out / dfeat).

@@ -40,6 +40,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "leaf_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "leaf_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "leaf_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "leaf_train_reserve": (c_int, [c_void_p, c_int]),
     "leaf_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
     "leaf_backward": (c_int, [c_void_p, c_void_p, ctypes.POINTER(LeafWeightPtrs), c_void_p]),

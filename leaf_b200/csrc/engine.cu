@@ -223,6 +223,7 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_BF16_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attb_smem_bytes(LEAF_CTX)));
   *out = e;
   return LEAF_OK;
@@ -539,6 +540,18 @@ extern "C" int leaf_score(leaf_handle_t e, const float* feat, const float* ancho
   if (static_cast<size_t>(n) * 4 > 48 * 1024) return fail(LEAF_ERR_INVALID, "n=%d too large", n);
   score_argmax_kernel<<<B, 256, static_cast<size_t>(n) * 4, static_cast<cudaStream_t>(stream)>>>(
       feat, anchor, n, e->cfg.embed_dim, objective, loss_out, best_out, best_feat_out);
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+extern "C" int leaf_topk(leaf_handle_t e, const float* score_a, const float* score_b, int32_t m, int32_t k, int32_t* idx_out,
+                         float* val_out, void* stream) {
+  if (!e || !score_a || !idx_out) return fail(LEAF_ERR_INVALID, "null argument");
+  if (m <= 0 || k <= 0 || k > m) return fail(LEAF_ERR_INVALID, "top-k of m=%d, k=%d", m, k);
+  const size_t smem = static_cast<size_t>(m) * 4;
+  if (smem > 200 * 1024) return fail(LEAF_ERR_INVALID, "m=%d too large (max %d)", m, 200 * 1024 / 4);
+  topk_kernel<<<1, 1024, smem, static_cast<cudaStream_t>(stream)>>>(score_a, score_b, m, k, idx_out, val_out);
   e->launches++;
   CK(cudaGetLastError());
   return LEAF_OK;

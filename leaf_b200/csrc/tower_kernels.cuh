@@ -459,6 +459,55 @@ __global__ void __launch_bounds__(256) score_argmax_kernel(const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Top-k of a score vector (Charmer's position selection, utils_attacks.py:519, and the argmax over the whole candidate
+// list, :447/:575, with k = 1). v[i] = a[i], or (a[i] + b[i]) / 2 when a second tower scores the same candidates
+// (:498-513). Order: value descending, ties by ascending index (torch.argmax's first-index rule for k = 1; torch.topk
+// leaves the order of ties unspecified). One CTA; the working copy of the scores lives in shared memory.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) topk_kernel(const float* __restrict__ a, const float* __restrict__ b, int m, int k,
+                                                    int* __restrict__ idx_out, float* __restrict__ val_out) {
+  extern __shared__ float tk[];     // [m]
+  __shared__ float red_v[32];
+  __shared__ int red_i[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) tk[i] = b ? (a[i] + b[i]) / 2.f : a[i];
+  __syncthreads();
+  for (int r = 0; r < k; ++r) {
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+      const float v = tk[i];
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[warp] = bv; red_i[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+      bv = lane < nwarp ? red_v[lane] : -INFINITY;
+      bi = lane < nwarp ? red_i[lane] : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+      }
+      if (lane == 0) {
+        if (bi == 0x7fffffff) bi = 0;             // every remaining score is -inf
+        idx_out[r] = bi;
+        if (val_out) val_out[r] = bv;
+        tk[bi] = -INFINITY;                       // taken (a genuine -inf score can be returned twice; not reachable here)
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // fp32 -> bf16 cast (weight refresh), optional transpose for text_projection [W,E] -> [E,W]
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;

@@ -271,6 +271,19 @@ class LeafEngine:
                                        _ptr(best_feat), _stream()))
         return best, best_feat, loss
 
+    def topk(self, score_a: torch.Tensor, k: int, m: int = None, score_b: torch.Tensor = None):
+        """Indices (int32 [k]) and values of the k largest of the first m scores; value descending, ties by ascending
+        index. score_b: a second tower's scores of the same candidates, averaged in (utils_attacks.py:498-513)."""
+        score_a = score_a.reshape(-1)
+        m = score_a.numel() if m is None else int(m)
+        if score_b is not None:
+            score_b = score_b.reshape(-1)
+        idx = torch.empty((k,), dtype=torch.int32, device=self.device)
+        val = torch.empty((k,), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_topk(self._h, _ptr(score_a), _ptr(score_b), m, int(k), _ptr(idx), _ptr(val), _stream()))
+        return idx, val
+
     # ---- hooks for tests / bench ---------------------------------------------------------------------------
     def gemm(self, A, Bt, bias=None, epilogue=0, act=0, C=None, m_dev=None):
         M, K = A.shape

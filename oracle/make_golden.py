@@ -181,7 +181,8 @@ def gen_eval_attacks():
     for ci, (si, n, k, objective, bs, two) in enumerate([
             (0, 10, 1, "l2", 2560, False), (1, 5, 2, "l2", 64, False), (2, 10, 1, "negl2", 2560, False),
             (3, 20, 3, "l2", 2560, False), (4, 3, 1, "sim", 2560, False), (5, 10, 1, "dissim", 100, False),
-            (6, 10, 1, "l2", 2560, False), (0, 6, 1, "dissim", 2560, True), (5, 4, 2, "sim", 2560, True)]):
+            (6, 10, 1, "l2", 2560, False), (0, 6, 1, "dissim", 2560, True), (5, 4, 2, "sim", 2560, True),
+            (5, 4, 2, "dissim", 2560, True), (1, 8, 2, "negl2", 2560, True)]):
         S = caps[si]
         norm = objective in ("sim", "dissim")
         with torch.no_grad():
@@ -190,7 +191,29 @@ def gen_eval_attacks():
             adv, dist = utils_attacks.attack_text_charmer_inference(
                 model, tok, S, anchor.clone(), "cpu", objective=objective, n=n, k=k, V=V, constrain=False, batch_size=bs,
                 model_2=model2 if two else None, model_2_anchor_features=anchor2.clone() if two else None)
-        charmer.append(dict(sentence=S, n=n, k=k, objective=objective, batch_size=bs, two=two, adv=adv, dist=dist))
+        # torch.topk / argmax on exactly equal scores (no-op edits all score like the sentence itself) make the
+        # reference's own result depend on the tie order of the torch build: flag those runs
+        from oracle import leaf_oracle as O
+        otok = O.OracleTokenizer()
+        enc = lambda t, normalize, sd_=sd: O.encode_text(sd_, t, cfg.heads, normalize=normalize)
+        enc2 = lambda t, normalize: O.encode_text(sd2, t, cfg.heads, normalize=normalize)
+        trace = {}
+        with torch.no_grad():
+            oadv, _ = O.attack_text_charmer_oracle(enc, otok, S, anchor.clone(), objective=objective, n=n, k=k, batch_size=bs,
+                                                   encode_2=enc2 if two else None,
+                                                   anchor_2=anchor2.clone() if two else None, trace=trace)
+        assert oadv == adv
+        tie = False
+        for r in trace["rounds"]:
+            v = torch.sort(r["loss1"], descending=True).values
+            kk = len(r["top"])
+            tie |= kk < len(v) and bool(v[kk - 1] == v[kk])      # WHICH positions are kept (their order only matters for a tied maximum)
+            # torch.argmax returns the FIRST maximum, so a tied maximum only depends on the torch build when the tied
+            # candidates sit at different kept positions whose own order was a tie
+            groups = set((torch.nonzero(r["loss2"] == r["loss2"].max()).flatten() // len(V)).tolist())
+            tie |= len(groups) > 1 and bool((v[:kk - 1] == v[1:kk]).any())
+        charmer.append(dict(sentence=S, n=n, k=k, objective=objective, batch_size=bs, two=two, adv=adv, dist=dist,
+                            tie_dependent=tie))
         arrays[f"charmer_anchor_{ci}"] = anchor.numpy()
         if two:
             arrays[f"charmer_anchor2_{ci}"] = anchor2.numpy()

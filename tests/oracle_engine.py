@@ -46,3 +46,11 @@ class OracleEngine:
         best = torch.argmax(loss, dim=-1)
         bf = f[torch.arange(B), best]
         return best.to(torch.int32), bf, (loss if want_loss else None)
+
+    def topk(self, score_a, k, m=None, score_b=None):
+        a = score_a.reshape(-1)
+        m = a.numel() if m is None else m
+        v = a[:m] if score_b is None else (a[:m] + score_b.reshape(-1)[:m]) / 2
+        order = sorted(range(m), key=lambda i: (-float(v[i]), i))[:k]       # value descending, ties by ascending index
+        idx = torch.tensor(order, dtype=torch.int32)
+        return idx, v[idx.long()]

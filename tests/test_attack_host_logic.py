@@ -36,6 +36,47 @@ def test_attack_driver_reproduces_reference_runs():
         assert np.abs(feats.numpy() - z[f"feats_{ci}"]).max() < 1e-4
 
 
+def _levenshtein(a, b):
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+def test_eval_attack_drivers_reproduce_reference_runs():
+    """leaf_b200.attack_text_charmer_inference / attack_text_bruteforce (host logic over the engine double) against
+    runs of the reference's own functions (utils_attacks.py:395-580), including the never-scored last candidate."""
+    from leaf_b200 import attack_text_bruteforce, attack_text_charmer_inference
+    g = json.load(open(os.path.join(GOLDEN, "eval_attack_golden.json")))
+    z = np.load(os.path.join(GOLDEN, "eval_attack_golden.npz"))
+    cfg = synth.TOWERS[g["tower"]]
+    eng = OracleEngine(synth.random_tower_state_dict(cfg, seed=g["seed"], exact_numpy=True), cfg.heads)
+    eng2 = OracleEngine(synth.random_tower_state_dict(cfg, seed=g["seed2"], exact_numpy=True), cfg.heads)
+    for ci, c in enumerate(g["charmer"]):
+        a2 = torch.from_numpy(z[f"charmer_anchor2_{ci}"]).clone() if c["two"] else None
+        adv, dist_ = attack_text_charmer_inference(eng, None, c["sentence"], torch.from_numpy(z[f"charmer_anchor_{ci}"]).clone(),
+                                                   "cpu", objective=c["objective"], n=c["n"], k=c["k"],
+                                                   batch_size=c["batch_size"], model_2=eng2 if c["two"] else None,
+                                                   model_2_anchor_features=a2)
+        if c["tie_dependent"]:        # the reference's own result hangs on torch.topk's unspecified order of equal scores
+            assert dist_ == c["dist"] and _levenshtein(adv, c["sentence"]) <= c["k"], ci
+        else:
+            assert (adv, dist_) == (c["adv"], c["dist"]), ci
+    for ci, c in enumerate(g["bruteforce"]):
+        adv, dist_ = attack_text_bruteforce(eng, None, c["sentence"], torch.from_numpy(z[f"brute_anchor_{ci}"]).clone(), "cpu",
+                                            batch_size=c["batch_size"], objective=c["objective"])
+        assert (adv, dist_) == (c["adv"], c["dist"]), ci
+    # the constraint mask: nothing valid -> the sentence comes back unchanged (utils_attacks.py:478-481, :532-537)
+    nothing_valid = lambda sentences, SS: [[False] * len(SS[0]) for _ in sentences]
+    c = g["charmer"][0]
+    adv, _ = attack_text_charmer_inference(eng, None, c["sentence"], torch.from_numpy(z["charmer_anchor_0"]).clone(), "cpu",
+                                           n=c["n"], k=1, constrain=nothing_valid)
+    assert adv == c["sentence"]
+
+
 def test_constraint_mask_replaces_candidates_by_the_current_sentence():
     g, z, cfg, sd = _setup()
     eng = OracleEngine(sd, cfg.heads)

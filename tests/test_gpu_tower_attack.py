@@ -238,3 +238,83 @@ def test_full_size_properties_vit_h():
     assert torch.equal(best.long(), loss.argmax(-1))
     assert torch.equal(loss[:, 7], loss[:, 3]) and not (best == 7).any()      # first index wins exact ties
     assert torch.equal(bf, f[torch.arange(B), best.long()])
+
+
+def test_topk_kernel():
+    """leaf_topk: value descending, ties by ascending index; optional second score vector averaged in; prefix length m."""
+    from leaf_b200 import synth
+    from leaf_b200.tower import LeafTextTower
+    eng = LeafTextTower.random("tiny", seed=0).leaf_engine
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for m_total, m, k in ((1, 1, 1), (97, 96, 10), (5000, 4999, 50), (20000, 19999, 1)):
+        a = torch.randn(m_total, generator=g, device="cuda")
+        a[torch.randint(0, m_total, (m_total // 3 + 1,), generator=g, device="cuda")] = 0.25     # plenty of exact ties
+        b = torch.randn(m_total, generator=g, device="cuda")
+        for sb in (None, b):
+            v = a[:m] if sb is None else (a[:m] + sb[:m]) / 2
+            order = sorted(range(m), key=lambda i, vv=v.cpu(): (-float(vv[i]), i))[:k]
+            idx, val = eng.topk(a, k, m=m, score_b=sb)
+            assert idx.cpu().tolist() == order
+            assert torch.equal(val.cpu(), v.cpu()[order])
+
+
+def test_eval_attacks_golden(golden_dir):
+    """attack_text_charmer_inference / attack_text_bruteforce on the engine against runs of the reference's own
+    functions (utils_attacks.py:395-580; tiny tower, fp32 CPU). The engine scores in bf16, so a decision only has to
+    match where the oracle's runner-up is further away than the stated loss tolerance."""
+    from leaf_b200 import attack_text_bruteforce, attack_text_charmer_inference, synth
+    from leaf_b200.tower import LeafTextTower
+    from oracle import leaf_oracle as O
+    g = json.load(open(os.path.join(golden_dir, "eval_attack_golden.json")))
+    z = np.load(os.path.join(golden_dir, "eval_attack_golden.npz"))
+    cfg = synth.TOWERS[g["tower"]]
+    sd = synth.random_tower_state_dict(cfg, seed=g["seed"], exact_numpy=True)
+    sd2 = synth.random_tower_state_dict(cfg, seed=g["seed2"], exact_numpy=True)
+    t1, t2 = LeafTextTower(sd, heads=cfg.heads), LeafTextTower(sd2, heads=cfg.heads)
+    otok = O.OracleTokenizer()
+    enc = lambda t, normalize: O.encode_text(sd, t, cfg.heads, normalize=normalize)
+    enc2 = lambda t, normalize: O.encode_text(sd2, t, cfg.heads, normalize=normalize)
+    nv = len(synth.V_DEFAULT)
+
+    def clear(loss, k):           # the k-th and (k+1)-th best scores are further apart than the tolerance
+        v = torch.sort(loss, descending=True).values
+        return k >= len(v) or bool((v[k - 1] - v[k]).abs() > LOSS_RTOL * v[k - 1].abs())
+
+    total = agree = 0
+    for ci, c in enumerate(g["charmer"]):
+        a1 = torch.from_numpy(z[f"charmer_anchor_{ci}"])
+        a2 = torch.from_numpy(z[f"charmer_anchor2_{ci}"]) if c["two"] else None
+        adv, dist_ = attack_text_charmer_inference(t1, None, c["sentence"], a1.clone().cuda(), "cuda", objective=c["objective"],
+                                                   n=c["n"], k=c["k"], batch_size=c["batch_size"],
+                                                   model_2=t2 if c["two"] else None,
+                                                   model_2_anchor_features=a2.clone().cuda() if c["two"] else None)
+        assert dist_ == c["dist"]
+        trace = {}
+        O.attack_text_charmer_oracle(enc, otok, c["sentence"], a1.clone(), objective=c["objective"], n=c["n"], k=c["k"],
+                                     batch_size=c["batch_size"], encode_2=enc2 if c["two"] else None,
+                                     anchor_2=a2.clone() if c["two"] else None, trace=trace)
+        decided = not c["tie_dependent"]
+        for r in trace["rounds"]:
+            # a clear cut between kept and dropped positions, and a winner clear of every candidate that is not its twin
+            l2 = r["loss2"]
+            twins = l2 >= l2.max() - 1e-6 * l2.max().abs()
+            rest = l2[~twins]
+            decided &= clear(r["loss1"], len(r["top"])) and (rest.numel() == 0 or bool(
+                (l2.max() - rest.max()).abs() > LOSS_RTOL * l2.max().abs()))
+        if decided:
+            total += 1
+            agree += int(adv == c["adv"])
+    for ci, c in enumerate(g["bruteforce"]):
+        a1 = torch.from_numpy(z[f"brute_anchor_{ci}"])
+        adv, dist_ = attack_text_bruteforce(t1, None, c["sentence"], a1.clone().cuda(), "cuda", batch_size=c["batch_size"],
+                                            objective=c["objective"])
+        assert dist_ == 1
+        trace = {}
+        O.attack_text_bruteforce_oracle(enc, otok, c["sentence"], a1.clone(), objective=c["objective"], trace=trace)
+        l = trace["loss"]
+        rest = l[l < l.max() - 1e-6 * l.max().abs()]
+        if bool((l.max() - rest.max()).abs() > LOSS_RTOL * l.max().abs()):
+            total += 1
+            agree += int(adv == c["adv"])
+    assert total >= 6, total
+    assert agree == total, (agree, total)
