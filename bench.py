@@ -257,28 +257,14 @@ def run_ours(a):
     #      headline; the headline metric stays "candidates scored per second" of the attack itself. ----
     train = None
     if not a.no_train_step:
-        tower.trainable()
-        params = [p for p in tower.parameters()]
-        opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4, betas=(0.9, 0.98), eps=1e-6, fused=True)   # scripts/train_leaf_vith.sh
+        from leaf_b200.fare import FareTrainer
+        frozen2 = LeafTextTower(synth.perturbed_copy(tower.open_clip_state_dict(), seed=1, std=1e-3), heads=cfg.heads,
+                                quick_gelu=cfg.quick_gelu, device=dev)
+        trainer = FareTrainer(tower, frozen2, rho=n, k_adv=k, lr=1e-5, wd=1e-4, beta1=0.9, beta2=0.98, eps=1e-6)   # scripts/train_leaf_vith.sh
 
         def train_step(seed):
             np.random.seed(seed)
-            with torch.no_grad():
-                _, adv = attack_text_leaf(tower, None, caps, anchor.clone(), dev, objective="l2", n=n, k=k)
-                tok = tower.tokenizer(adv)
-            f = tower.encode_text(tok)
-            loss = torch.nn.functional.mse_loss(anchor, f, reduction="none").sum(-1).mean()
-            loss.backward()
-            if world > 1:
-                flat = torch.cat([p.grad.flatten() for p in params])
-                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-                off = 0
-                for p in params:
-                    p.grad.copy_(flat[off:off + p.numel()].view_as(p))
-                    off += p.numel()
-            opt.step()
-            opt.zero_grad(set_to_none=True)
-            tower.refresh()
+            loss, _ = trainer.step(caps)
             return float(loss.item())
 
         train_step(3000)
@@ -292,10 +278,11 @@ def run_ours(a):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         train = dict(ms_per_step=tt.item(), attack_ms_per_step=e2e_ms / a.steps, loss_first=losses[0], loss_last=losses[-1],
-                     what="attack_text_leaf + tokenize winners + forward/backward (K4) + "
-                          + ("NCCL all-reduce + " if world > 1 else "") + "fused AdamW + weight refresh")
+                     what="leaf_b200.fare.FareTrainer.step: frozen anchors + attack_text_leaf + tokenize winners + forward/backward "
+                          "(K4, gradients accumulated into one flat buffer) + " + ("NCCL all-reduce + " if world > 1 else "")
+                          + "native AdamW (one launch) + weight refresh")
         tower.trainable(False)
-        opt = None
+        del trainer, frozen2
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): one extra step with CUDA events around every GEMM launch ----
     eng.set_timing(True)

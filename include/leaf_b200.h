@@ -155,6 +155,16 @@ int leaf_train_reserve(leaf_handle_t h, int32_t max_seqs);
 int leaf_forward_train(leaf_handle_t h, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out, void* stream);
 int leaf_backward(leaf_handle_t h, const float* dfeat, const leaf_weight_ptrs_t* grads, void* stream);
 
+/* AdamW (torch.optim.AdamW semantics, decoupled weight decay) over the tower's parameters held in ONE flat fp32 buffer
+ * (train_AT_text_only.py:326-341: the gain / bias / LayerNorm group with weight_decay 0 is laid out first, elements
+ * [0, n_nodecay); utils_AT.py:358-362). grads are multiplied by grad_scale first (1/accum_freq, or a clipping
+ * coefficient). step >= 1 is the bias-correction step count. One launch, 28 B of HBM traffic per parameter.
+ * leaf_sumsq adds the sum of squares of a flat buffer into out[0] (gradient-norm clipping, utils_AT.py:349-357). */
+int leaf_adamw(leaf_handle_t h, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+               int64_t n_nodecay, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+               float grad_scale, void* stream);
+int leaf_sumsq(leaf_handle_t h, const float* g, int64_t n, float* out, void* stream);
+
 /* ---- test / bench hooks (used by tests/ and bench.py only) ------------------------------------ */
 /* C[M,N] = A[M,K] . Bt[N,K]^T (+bias[N]) with the tower's tcgen05 kernel. epilogue: 0 = bf16 store,
  * 1 = bf16 store after activation `act`, 2 = fp32 C += result (residual), 3 = fp32 store.

@@ -900,3 +900,32 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
   CK(cudaGetLastError());
   return LEAF_OK;
 }
+
+// AdamW step over a flat fp32 parameter buffer (n a multiple of 4, 16-byte aligned): train_AT_text_only.py:326-341,
+// utils_AT.py:358-362. Elements [0, n_nodecay) take no weight decay.
+extern "C" int leaf_adamw(leaf_handle_t e, float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                          int64_t n_nodecay, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
+                          float grad_scale, void* stream) {
+  if (!e || !params || !grads || !exp_avg || !exp_avg_sq) return fail(LEAF_ERR_INVALID, "null argument");
+  if (n <= 0 || n % 4 != 0 || n_nodecay < 0 || n_nodecay > n || step < 1) return fail(LEAF_ERR_INVALID, "n=%lld n_nodecay=%lld step=%d", (long long)n, (long long)n_nodecay, step);
+  if ((reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grads) | reinterpret_cast<uintptr_t>(exp_avg) |
+       reinterpret_cast<uintptr_t>(exp_avg_sq)) & 15)
+    return fail(LEAF_ERR_INVALID, "AdamW buffers must be 16-byte aligned");
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2s = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+  adamw_kernel<<<launch_ew(e, static_cast<size_t>(n) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      params, grads, exp_avg, exp_avg_sq, static_cast<size_t>(n), static_cast<size_t>(n_nodecay), lr, beta1, beta2, eps,
+      weight_decay, bc1, bc2s, grad_scale);
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+// out[0] (device fp32, zeroed by the caller) += sum of squares of g[0, n)
+extern "C" int leaf_sumsq(leaf_handle_t e, const float* g, int64_t n, float* out, void* stream) {
+  if (!e || !g || !out || n <= 0 || n % 4 != 0) return fail(LEAF_ERR_INVALID, "bad argument");
+  sumsq_kernel<<<launch_ew(e, static_cast<size_t>(n) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, static_cast<size_t>(n), out);
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}

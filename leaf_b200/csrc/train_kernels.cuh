@@ -267,6 +267,53 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int* __restrict__ 
   }
 }
 
+// ---- AdamW over the tower's flat parameter buffer (torch.optim.AdamW semantics, decoupled weight decay;
+// train_AT_text_only.py:326-341: gains / biases / LayerNorm parameters form a group with weight_decay = 0 and are laid
+// out first, elements [0, n_nodecay)). g is multiplied by grad_scale first (1/accum_freq, or the clipping
+// coefficient). bc1 = 1 - beta1^t, bc2s = sqrt(1 - beta2^t). HBM bound: 28 B per element.
+__global__ void __launch_bounds__(256) adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                    float* __restrict__ v, size_t n, size_t n_nodecay, float lr, float beta1,
+                                                    float beta2, float eps, float wd, float bc1, float bc2s, float grad_scale) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    float4 pv = *reinterpret_cast<const float4*>(p + i), gv = *reinterpret_cast<const float4*>(g + i);
+    float4 mv = *reinterpret_cast<const float4*>(m + i), vv = *reinterpret_cast<const float4*>(v + i);
+    float* pp = &pv.x; float* gg = &gv.x; float* mm = &mv.x; float* vs = &vv.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float gj = gg[j] * grad_scale;
+      if (i + j >= n_nodecay) pp[j] *= 1.f - lr * wd;
+      mm[j] = beta1 * mm[j] + (1.f - beta1) * gj;              // lerp(m, g, 1 - beta1)
+      vs[j] = beta2 * vs[j] + (1.f - beta2) * gj * gj;
+      const float denom = sqrtf(vs[j]) / bc2s + eps;
+      pp[j] -= (lr / bc1) * (mm[j] / denom);
+    }
+    *reinterpret_cast<float4*>(p + i) = pv;
+    *reinterpret_cast<float4*>(m + i) = mv;
+    *reinterpret_cast<float4*>(v + i) = vv;
+  }
+}
+
+// sum of squares of a flat fp32 buffer (gradient-norm clipping, utils_AT.py:349-357): out[0] += sum(g^2)
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, size_t n, float* __restrict__ out) {
+  __shared__ float part[8];
+  float s = 0.f;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    const float4 v = *reinterpret_cast<const float4*>(g + i);
+    s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += part[i];
+    atomicAdd(out, t);
+  }
+}
+
 // dst[r, :] += src[r, :] (fp32), used to add the attention/MLP branch gradient into the running dx
 __global__ void add_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)

@@ -1,0 +1,101 @@
+"""The LEAF / TextFARE training iteration on the engine: the body of train_one_epoch_text_only's batch loop
+(/root/reference/utils_AT.py:291-366) - frozen anchor, LEAF attack, forward + backward of the B winners, gradient
+accumulation, clipping, AdamW with the reference's two parameter groups (/root/reference/train_AT_text_only.py:326-341)
+and, under torch.distributed, the data-parallel gradient all-reduce the reference delegates to DDP.
+
+What is native: everything that touches the tower (K1-K4), the AdamW update (one launch over the flat parameter
+buffer), the gradient-norm reduction. What stays torch: the two-line loss expression and the NCCL all-reduce call.
+The scheduler, the data loader, logging and checkpointing are the caller's, unchanged (out of scope).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+import torch.distributed as dist
+
+from ._native import check
+from .attack import V_DEFAULT, attack_text_leaf
+from .engine import _ptr, _stream
+from .eval_attacks import attack_text_charmer_inference
+from .tower import LeafTextTower
+
+
+class FareTrainer:
+    """One object per process (GPU). Hyper-parameters carry the reference's names (params_AT.py, scripts/train_leaf_*.sh):
+    lr, wd, beta1, beta2, eps, accum_freq, grad_clip_norm, rho, k_adv, constrain, normalize_fare, use_charmer."""
+
+    def __init__(self, tower: LeafTextTower, frozen: LeafTextTower, V=V_DEFAULT, rho: int = 50, k_adv: int = 1, lr: float = 1e-5,
+                 wd: float = 1e-4, beta1: float = 0.9, beta2: float = 0.98, eps: float = 1e-6, accum_freq: int = 1,
+                 grad_clip_norm: float = None, constrain=False, normalize_fare: bool = False, use_charmer: bool = False,
+                 group=None):
+        self.tower, self.frozen, self.V = tower, frozen, list(V)
+        self.rho, self.k_adv, self.constrain = rho, k_adv, constrain
+        self.lr, self.wd, self.beta1, self.beta2, self.eps = lr, wd, beta1, beta2, eps
+        self.accum_freq, self.grad_clip_norm = accum_freq, grad_clip_norm
+        self.normalize_fare, self.use_charmer, self.group = normalize_fare, use_charmer, group
+        tower.trainable()
+        tower.attach_grads()
+        tower.zero_grad()
+        self.exp_avg = torch.zeros_like(tower.flat_params)
+        self.exp_avg_sq = torch.zeros_like(tower.flat_params)
+        self._norm = torch.zeros(1, dtype=torch.float32, device=tower.flat_params.device)
+        self.opt_step = 0            # optimizer steps taken
+        self.micro = 0               # micro-batches seen
+
+    # ---- pieces (public so that a caller can keep its own loop and swap single stages) -------------------------------
+    @torch.no_grad()
+    def anchors(self, texts):
+        """utils_AT.py:296."""
+        return self.frozen.encode_text(self.frozen.tokenizer(texts), normalize=self.normalize_fare)
+
+    @torch.no_grad()
+    def attack(self, texts, anchors):
+        """utils_AT.py:297-309."""
+        dev = self.tower.flat_params.device
+        if self.use_charmer:
+            return [attack_text_charmer_inference(self.tower, None, t, anchors[j], dev, objective="l2", n=self.rho, k=self.k_adv,
+                                                  constrain=self.constrain, V=self.V)[0] for j, t in enumerate(texts)]
+        return attack_text_leaf(self.tower, None, texts, anchors, dev, objective="l2", n=self.rho, k=self.k_adv, V=self.V,
+                                constrain=self.constrain)[1]
+
+    def lr_at(self, step: int) -> float:
+        """Hook for the caller's scheduler (utils_AT.py:287-288); constant by default."""
+        return self.lr
+
+    def optimizer_step(self, grad_scale: float = 1.0):
+        """utils_AT.py:338-362 with scaler = None: all-reduce (DDP's job in the reference), clip, AdamW, zero_grad; then the
+        engine re-casts its bf16 operand copies from the updated fp32 parameters."""
+        t = self.tower
+        g, eng = t.flat_grads, t.leaf_engine
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+        scale = grad_scale
+        if self.grad_clip_norm is not None:                       # torch.nn.utils.clip_grad_norm_, norm_type 2
+            self._norm.zero_()
+            check(eng._lib.leaf_sumsq(eng._h, _ptr(g), g.numel(), _ptr(self._norm), _stream()))
+            total = math.sqrt(float(self._norm.item())) * grad_scale
+            scale *= min(1.0, self.grad_clip_norm / (total + 1e-6))
+        self.opt_step += 1
+        f = ctypes.c_float
+        check(eng._lib.leaf_adamw(eng._h, _ptr(t.flat_params), _ptr(g), _ptr(self.exp_avg), _ptr(self.exp_avg_sq), g.numel(),
+                                  t.n_nodecay, f(self.lr_at(self.opt_step)), f(self.beta1), f(self.beta2), f(self.eps), f(self.wd),
+                                  self.opt_step, f(scale), _stream()))
+        t.zero_grad()
+        t.refresh()
+
+    # ---- the iteration ---------------------------------------------------------------------------------------------------
+    def step(self, texts):
+        """One micro-batch of utils_AT.py:291-366. Returns (loss_FARE_text as a 0-d tensor, adversarial texts)."""
+        t = self.tower
+        anchors = self.anchors(texts)
+        adv_texts = self.attack(texts, anchors.clone())
+        tok = t.tokenizer(adv_texts)                                                       # :312
+        feats = t.encode_text(tok, normalize=self.normalize_fare)                          # :317-319 (train mode == eval: no dropout)
+        loss = torch.nn.functional.mse_loss(anchors, feats, reduction="none").sum(dim=-1).mean()      # :321-322
+        (loss / self.accum_freq).backward()                                                # :329-337
+        self.micro += 1
+        if self.micro % self.accum_freq == 0:
+            self.optimizer_step()
+        return loss.detach(), adv_texts

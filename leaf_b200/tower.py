@@ -3,6 +3,12 @@ and whose forward runs on the native engine. It offers the two duck-typed member
 
     tower.encode_text(tokens, normalize=False) -> Tensor[N,E]     /root/reference/src/open_clip/model.py:269-284
     tower.tokenizer(list[str]) -> LongTensor[N,77]                 /root/reference/src/open_clip/tokenizer.py:226-265
+
+Memory layout: every parameter is a view into ONE flat fp32 buffer, and (once trainable) every .grad a view into a
+second one. The parameters the reference's optimizer puts in its weight_decay = 0 group come first
+(train_AT_text_only.py:329: `p.ndim < 2 or "bn" in n or "ln" in n or "bias" in n or "logit_scale" in n`), so the FARE
+update is one AdamW launch over the flat buffers, the data-parallel gradient exchange one all-reduce, and zeroing the
+gradients one memset (leaf_b200/fare.py).
 """
 from __future__ import annotations
 
@@ -12,34 +18,50 @@ from . import synth
 from .engine import LeafEngine
 
 
+def no_weight_decay(name: str, ndim: int) -> bool:
+    """train_AT_text_only.py:329."""
+    return ndim < 2 or "bn" in name or "ln" in name or "bias" in name or "logit_scale" in name
+
+
 class _EncodeTextTrain(torch.autograd.Function):
-    """encode_text under autograd: forward = leaf_forward_train, backward = leaf_backward. The parameters are inputs of
-    the Function so that autograd accumulates the returned gradients into their .grad, like any torch module."""
+    """encode_text under autograd: forward = leaf_forward_train, backward = leaf_backward, which ACCUMULATES straight into
+    the parameters' .grad (views of the tower's flat gradient buffer) - no per-parameter temporaries, no 390 tiny
+    add kernels. The parameters are inputs of the Function only so that autograd knows the output needs a backward."""
 
     @staticmethod
     def forward(ctx, tower, tok, *params):
         ctx.tower = tower
-        ctx.needs = [p.requires_grad for p in params]
         return tower.leaf_engine.forward_train(tok)
 
     @staticmethod
     def backward(ctx, dfeat):
         tower = ctx.tower
-        names = list(tower._names)
-        grads = {k: torch.zeros_like(getattr(tower, tower._names[k]).data) for k in names}
+        tower.attach_grads()
+        grads = {k: (p.grad if p.requires_grad else None) for k, p in tower.named_tower_parameters()}
         tower.leaf_engine.backward(dfeat, grads)
-        return (None, None) + tuple(grads[k] if need else None for k, need in zip(names, ctx.needs))
+        return (None, None) + (None,) * len(grads)
 
 
 class LeafTextTower(torch.nn.Module):
     def __init__(self, state_dict: dict, heads: int, quick_gelu: bool = False, device="cuda"):
         super().__init__()
-        self._names = {}
-        for k, v in state_dict.items():
+        items = sorted(state_dict.items(), key=lambda kv: 0 if no_weight_decay(kv[0], kv[1].dim()) else 1)   # stable
+        sizes = [(v.numel() + 3) // 4 * 4 for _, v in items]                     # 16-byte aligned slices
+        self._flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
+        self._gflat = None
+        self._names, self._slices = {}, {}
+        off = 0
+        self.n_nodecay = 0
+        for (k, v), sz in zip(items, sizes):
+            view = self._flat[off:off + v.numel()].view(v.shape)
+            view.copy_(v.detach().to(device=device, dtype=torch.float32))
             safe = k.replace(".", "__")
             self._names[k] = safe
-            self.register_parameter(safe, torch.nn.Parameter(v.detach().to(device=device, dtype=torch.float32).contiguous(),
-                                                             requires_grad=False))
+            self._slices[k] = (off, v.numel(), tuple(v.shape))
+            self.register_parameter(safe, torch.nn.Parameter(view, requires_grad=False))
+            off += sz
+            if no_weight_decay(k, v.dim()):
+                self.n_nodecay = off
         self.heads, self.quick_gelu = heads, quick_gelu
         self.leaf_engine = LeafEngine(self.open_clip_state_dict(), heads=heads, quick_gelu=quick_gelu)
 
@@ -50,8 +72,48 @@ class LeafTextTower(torch.nn.Module):
         sd = synth.random_tower_state_dict(cfg, seed=seed, device="cpu" if exact_numpy else device, exact_numpy=exact_numpy)
         return cls(sd, heads=cfg.heads, quick_gelu=cfg.quick_gelu, device=device)
 
+    # ---- parameters ------------------------------------------------------------------------------------------
+    def named_tower_parameters(self):
+        return [(k, getattr(self, safe)) for k, safe in self._names.items()]
+
     def open_clip_state_dict(self) -> dict:
         return {k: getattr(self, safe).data for k, safe in self._names.items()}
+
+    @property
+    def flat_params(self) -> torch.Tensor:
+        return self._flat
+
+    @property
+    def flat_grads(self) -> torch.Tensor:
+        if self._gflat is None:
+            self._gflat = torch.zeros_like(self._flat)
+        return self._gflat
+
+    def attach_grads(self):
+        """Make every trainable parameter's .grad the matching view of the flat gradient buffer. A .grad that is None
+        (fresh, or after optimizer.zero_grad(set_to_none=True)) starts from zero."""
+        g = self.flat_grads
+        params = [(k, p) for k, p in self.named_tower_parameters() if p.requires_grad]
+        if all(p.grad is None for _, p in params):
+            g.zero_()
+        for k, p in params:
+            off, n, shape = self._slices[k]
+            view = g[off:off + n].view(shape)
+            if p.grad is None:
+                if not all(q.grad is None for _, q in params):
+                    view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+
+    def zero_grad(self, set_to_none: bool = False):
+        """One memset of the flat buffer; the .grad views stay attached."""
+        if self._gflat is not None:
+            self._gflat.zero_()
+        if set_to_none:
+            for p in self.parameters():
+                p.grad = None
 
     def refresh(self):
         """Call after the parameters changed (optimizer step)."""
@@ -70,7 +132,7 @@ class LeafTextTower(torch.nn.Module):
         """model.py:269-284. Under torch.no_grad() (the attack, utils_AT.py:295) this is the inference path; with
         gradients enabled and trainable parameters (utils_AT.py:317-319) the forward keeps its activations and
         loss.backward() runs the engine's backward. Call refresh() after optimizer.step()."""
-        params = [getattr(self, safe) for safe in self._names.values()]
+        params = [p for _, p in self.named_tower_parameters()]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             f = _EncodeTextTrain.apply(self, text, *params)
             return torch.nn.functional.normalize(f, dim=-1) if normalize else f

@@ -19,8 +19,8 @@ tower = LeafTextTower.random(model, seed=0).trainable()
 caps = synth.make_captions(B, seed=100)
 with torch.no_grad():
     anchor = tower.encode_text(tower.tokenizer(caps)) + 0.01
-params = list(tower.parameters())
-opt = torch.optim.AdamW(params, lr=1e-5, weight_decay=1e-4, betas=(0.9, 0.98), eps=1e-6, fused=True)
+from leaf_b200.fare import FareTrainer  # noqa: E402
+trainer = FareTrainer(tower, tower, rho=n, k_adv=1)
 acc = {}
 
 
@@ -41,9 +41,7 @@ def step(seed):
     f = stage("forward (train)", lambda: tower.encode_text(tok))
     loss = stage("loss", lambda: torch.nn.functional.mse_loss(anchor, f, reduction="none").sum(-1).mean())
     stage("backward", loss.backward)
-    stage("optimizer", opt.step)
-    stage("zero_grad", lambda: opt.zero_grad(set_to_none=True))
-    stage("refresh", tower.refresh)
+    stage("optimizer (AdamW + zero_grad + refresh)", trainer.optimizer_step)
 
 
 step(0)
