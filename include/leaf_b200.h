@@ -114,6 +114,21 @@ int leaf_expand_tokenize(leaf_handle_t h, const uint8_t* caps, const int32_t* ca
                          const int32_t* pos, const int32_t* chr, const int32_t* sel, const uint8_t* valid,
                          int32_t* tok_out, int32_t* len_out, int32_t* base_out, int32_t* status_out, void* stream);
 
+/* ---- the `--constrain` filter on the device ---------------------------------------------------------
+ * Replaces valid_sentence_batched (utils_attacks.py:110-143; applied at :321-325, :360-364, :478-481, :532-537):
+ * valid[b,j] = len(W & set(word_tokenize(candidate.lower()))) < len(W & set(word_tokenize(sentence_b.lower()))).
+ * leaf_load_words takes W (the reference: nltk.corpus.words.words()) and, optionally, Punkt's abbreviation types, as
+ * HOST byte blobs with [n+1] offsets, and keeps them as hash sets on the device. leaf_constrain_mask has
+ * leaf_expand_tokenize's candidate arguments; valid_out [B,n] uint8 feeds leaf_expand_tokenize's `valid`;
+ * count_out [B*n+B] (may be NULL) receives the dictionary-word counts (candidates, then the B sentences).
+ * word_tokenize is NLTK's: the Treebank substitutions are restated one by one (exact by construction), Punkt's sentence
+ * split is approximated - PARITY UNPINNED against NLTK, which cannot be installed here (csrc/constrain_core.cuh). */
+int leaf_load_words(leaf_handle_t h, const uint8_t* words_blob, const int32_t* words_off, int32_t n_words,
+                    const uint8_t* abbrev_blob, const int32_t* abbrev_off, int32_t n_abbrev);
+int leaf_constrain_mask(leaf_handle_t h, const uint8_t* caps, const int32_t* cap_off, int32_t B, int32_t n,
+                        const int32_t* pos, const int32_t* chr, const int32_t* sel, uint8_t* valid_out,
+                        int32_t* count_out, int32_t* status_out, void* stream);
+
 /* ---- K2: text tower forward -------------------------------------------------------------------
  * Replaces CLIP.encode_text(tokens, normalize) (model.py:269-284; transformer.py:254-265,355-366,
  * 653-665). tok [N,77] int32, len [N] (positions after argmax(ids) are dead under the causal mask and

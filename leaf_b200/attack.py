@@ -84,8 +84,9 @@ def _engine_of(model) -> LeafEngine:
 
 def _valid_mask(constrain, sentences, SS, B, n, device):
     """utils_attacks.py:321-325 / :360-364: candidates failing the constraint are replaced by the current sentence.
-    The reference's filter (valid_sentence_batched, :110-143) needs NLTK corpora; here it is a host callable
-    constrain(sentences, SS) -> bool[B][n] supplied by the caller (parity unpinned)."""
+    constrain=True runs the filter on the device (engine.load_words + leaf_constrain_mask); a callable
+    constrain(sentences, SS) -> bool[B][n] (e.g. the reference's own valid_sentence_batched, :110-143, which needs the
+    NLTK corpora) is evaluated on the host from the candidate strings."""
     valid = np.asarray(constrain(sentences, SS), dtype=np.uint8).reshape(B, n)
     return _to_dev(valid, device)
 
@@ -103,8 +104,10 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
     if shard not in (None, "samples", "candidates"):
         raise ValueError(f"unknown shard mode {shard!r}")
     eng = _engine_of(model)
-    if constrain is True:
-        raise LeafError("constrain=True needs the reference's NLTK word list, which cannot be reproduced offline; pass "
+    on_device = constrain is True
+    if on_device and not getattr(eng, "has_words", False):
+        raise LeafError("constrain=True needs the word list of the reference's filter (NLTK data, not reproducible offline): "
+                        "call engine.load_words(nltk.corpus.words.words()) once, or pass "
                         "constrain=<callable(sentences, SS) -> bool[B][n]> (e.g. utils_attacks.valid_sentence_batched)")
     valid_fn = constrain if callable(constrain) else None
     sentences = list(sentences)
@@ -144,7 +147,7 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
             host_d = _to_dev(host, dev)
             pos_d, chr1_d, chr2_d = host_d[:Bl * nl], host_d[Bl * nl:2 * Bl * nl], host_d[2 * Bl * nl:]
             # --- phase 1: choose the position (a space at each drawn z), :316-353 ---
-            valid1 = None
+            valid1 = eng.constrain_mask(caps_d, off_d, Bl, nl, pos_d, chr1_d) if on_device else None     # :321-325
             if valid_fn is not None:
                 SS = [[generate_sentence(S, int(z), 32) for z in pos_l[i]] for i, S in enumerate(mine)]
                 valid1 = _valid_mask(valid_fn, mine, SS, Bl, nl, dev)
@@ -161,7 +164,7 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
             g1, pos2_d, sel = best1.long(), pos_d, best1
         if Bl > 0 and nl > 0:
             # --- phase 2: choose the character at the best position, :355-389 ---
-            valid2 = None
+            valid2 = eng.constrain_mask(caps_d, off_d, Bl, nl, pos2_d, chr2_d, sel) if on_device else None   # :360-364
             if valid_fn is not None:
                 zs_l = positions[np.arange(blo, bhi), g1.cpu().numpy()]
                 SS = [[generate_sentence(S, int(zs_l[i]), int(c)) for c in chr2_l[i]] for i, S in enumerate(mine)]

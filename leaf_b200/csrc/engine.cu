@@ -18,6 +18,7 @@
 #include "gemm2_sm100.cuh"
 #include "gemm_sm100.cuh"
 #include "k1_tables_host.h"
+#include "constrain_kernel.cuh"
 #include "k1_tokenize.cuh"
 #include "tower_kernels.cuh"
 #include "train_kernels.cuh"
@@ -81,6 +82,11 @@ struct leaf_engine {
   bool bpe_loaded = false;
   std::vector<void*> table_allocs;
   K1Tables tables{};
+  // --constrain filter: hash sets of the word list and of Punkt abbreviation types
+  CnTables cn{};
+  bool words_loaded = false;
+  int32_t* cn_count = nullptr;
+  int cn_count_cap = 0;
   // weights
   bool bound = false;
   leaf_weight_ptrs_t wp{};
@@ -260,6 +266,7 @@ extern "C" int leaf_destroy(leaf_handle_t e) {
   e->tw = TrainWs();
   free_weights(e);
   for (void* p : e->table_allocs) cudaFree(p);
+  cudaFree(e->cn_count);
   for (auto& sp : e->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
   for (auto ev : e->event_pool) cudaEventDestroy(ev);
   delete e;
@@ -926,6 +933,51 @@ extern "C" int leaf_sumsq(leaf_handle_t e, const float* g, int64_t n, float* out
   if (!e || !g || !out || n <= 0 || n % 4 != 0) return fail(LEAF_ERR_INVALID, "bad argument");
   sumsq_kernel<<<launch_ew(e, static_cast<size_t>(n) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, static_cast<size_t>(n), out);
   e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+// ---- on-device --constrain filter (constrain_core.cuh) ---------------------------------------------------------------------
+extern "C" int leaf_load_words(leaf_handle_t e, const uint8_t* words_blob, const int32_t* words_off, int32_t n_words,
+                               const uint8_t* abbrev_blob, const int32_t* abbrev_off, int32_t n_abbrev) {
+  if (!e || !words_blob || !words_off || n_words <= 0) return fail(LEAF_ERR_INVALID, "word list required");
+  if (n_abbrev > 0 && (!abbrev_blob || !abbrev_off)) return fail(LEAF_ERR_INVALID, "abbreviation list");
+  CnTables T{};
+  std::vector<uint64_t> w = cn_build_table(words_blob, words_off, n_words, &T.words_bits);
+  int rc;
+  if ((rc = upload(e, w.data(), w.size(), &T.words))) return rc;
+  if (n_abbrev > 0) {
+    std::vector<uint64_t> ab = cn_build_table(abbrev_blob, abbrev_off, n_abbrev, &T.abbrev_bits);
+    if ((rc = upload(e, ab.data(), ab.size(), &T.abbrev))) return rc;
+  }
+  e->cn = T;
+  e->words_loaded = true;
+  return LEAF_OK;
+}
+
+extern "C" int leaf_constrain_mask(leaf_handle_t e, const uint8_t* caps, const int32_t* cap_off, int32_t B, int32_t n,
+                                   const int32_t* pos, const int32_t* chr, const int32_t* sel, uint8_t* valid_out,
+                                   int32_t* count_out, int32_t* status_out, void* stream) {
+  if (!e || !caps || !cap_off || !pos || !chr || !valid_out) return fail(LEAF_ERR_INVALID, "null argument");
+  if (!e->words_loaded) return fail(LEAF_ERR_STATE, "leaf_load_words has not been called");
+  if (B <= 0 || n <= 0) return fail(LEAF_ERR_INVALID, "B=%d n=%d", B, n);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int R = B * n + B;
+  int32_t* cnt = count_out;
+  if (!cnt) {
+    if (R > e->cn_count_cap) {
+      CK(cudaStreamSynchronize(st));
+      cudaFree(e->cn_count);
+      e->cn_count = nullptr;
+      CK(cudaMalloc(&e->cn_count, static_cast<size_t>(R) * 4));
+      e->cn_count_cap = R;
+    }
+    cnt = e->cn_count;
+  }
+  CnArgs a{caps, cap_off, B, n, pos, chr, sel, cnt, status_out};
+  constrain_count_kernel<<<(R + 63) / 64, 64, 0, st>>>(e->cn, a);
+  constrain_valid_kernel<<<(B * n + 255) / 256, 256, 0, st>>>(cnt, B, n, valid_out);
+  e->launches += 2;
   CK(cudaGetLastError());
   return LEAF_OK;
 }

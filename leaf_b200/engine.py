@@ -107,6 +107,7 @@ class LeafEngine:
             check(self._lib.leaf_load_bpe(self._h, pairs.ctypes.data_as(ctypes.c_void_p), len(pairs)))
             self._bind()
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.has_words = False
         self.max_seqs = 0
         if max_seqs:
             self.reserve(max_seqs)
@@ -197,13 +198,43 @@ class LeafEngine:
                                                  _ptr(valid), _ptr(tok), _ptr(ln), _ptr(base), _ptr(self._status), _stream()))
         return tok, ln, base
 
+    # ---- --constrain on the device ----------------------------------------------------------------------------------
+    @staticmethod
+    def _pack_words(words):
+        blobs = [w.encode("ascii") for w in words if w.isascii()]
+        off = np.zeros(len(blobs) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(b) for b in blobs])
+        return np.frombuffer(b"".join(blobs) + b"\0", dtype=np.uint8).copy(), off, len(blobs)
+
+    def load_words(self, words, abbrev=()):
+        """The dictionary W of the reference's filter (utils_attacks.py:125: set(nltk.corpus.words.words())) and,
+        optionally, Punkt's abbreviation types (nltk ... PunktSentenceTokenizer._params.abbrev_types). After this,
+        attack_text_leaf(..., constrain=True) computes the validity masks on the device."""
+        wb, wo, nw = self._pack_words(words)
+        ab, ao, na = self._pack_words(abbrev)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_load_words(self._h, p(wb), p(wo), nw, p(ab) if na else None, p(ao) if na else None, na))
+        self.has_words = True
+
+    def constrain_mask(self, caps_dev, off_dev, B, n, pos, chr_, sel=None, want_counts=False):
+        """valid uint8 [B,n] (and the int32 dictionary-word counts [B*n+B]) for the candidates of expand_tokenize."""
+        valid = torch.empty((B, n), dtype=torch.uint8, device=self.device)
+        counts = torch.empty((B * n + B,), dtype=torch.int32, device=self.device) if want_counts else None
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_constrain_mask(self._h, _ptr(caps_dev), _ptr(off_dev), B, n, _ptr(pos), _ptr(chr_), _ptr(sel),
+                                                _ptr(valid), _ptr(counts), _ptr(self._status), _stream()))
+        return (valid, counts) if want_counts else valid
+
     def check_status(self):
         """Synchronising read of the tokenizer status flags; raises on inputs outside the kernel's closed domain."""
         st = int(self._status.item())
         if st:
             self._status.zero_()
             what = [m for bit, m in ((1, "an html entity expanded outside U+0000..U+00FF"),
-                                     (2, "non-ASCII caption byte"), (4, "caption too long / position out of range")) if st & bit]
+                                     (2, "non-ASCII caption byte"), (4, "caption too long / position out of range"),
+                                     (8, "sentence longer than the constraint filter accepts (511 bytes)"),
+                                     (16, "constraint filter buffer overflow")) if st & bit]
             raise LeafError("tokenizer kernel: " + "; ".join(what))
 
     def tokenize(self, texts, check=True) -> torch.Tensor:

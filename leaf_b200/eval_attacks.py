@@ -27,7 +27,7 @@ from .attack import V_DEFAULT, _engine_of, _to_dev, generate_sentence
 from .engine import OBJECTIVES
 
 
-def _score_list(eng, eng2, sentence, pos, chr_, anchor, anchor2, objective, valid=None):
+def _score_list(eng, eng2, sentence, pos, chr_, anchor, anchor2, objective, valid=None, device_filter=False):
     """Scores of the candidate list {(pos[g,j], chr_[g,j])} of ONE sentence. The list is laid out as `groups` samples of
     `per` candidates that all hold the same caption (per = len(V) when positions repeat per character), so the tower's
     shared-prefix reuse and in-group duplicate elimination apply. `pos` may already live on the device (the top-k
@@ -38,6 +38,8 @@ def _score_list(eng, eng2, sentence, pos, chr_, anchor, anchor2, objective, vali
     pos_d = pos if torch.is_tensor(pos) else _to_dev(np.ascontiguousarray(pos, dtype=np.int32), dev)
     chr_d = _to_dev(np.ascontiguousarray(chr_, dtype=np.int32), dev)
     valid_d = None if valid is None else _to_dev(np.ascontiguousarray(valid, dtype=np.uint8), dev)
+    if device_filter:                                                          # constrain=True: the mask never leaves the device
+        valid_d = eng.constrain_mask(caps_d, off_d, groups, per, pos_d, chr_d)
     eng.reserve(groups * per + groups)
     tok, ln, base = eng.expand_tokenize(caps_d, off_d, groups, per, pos=pos_d, chr_=chr_d, valid=valid_d)
     norm = objective in ("sim", "dissim")
@@ -50,7 +52,7 @@ def _score_list(eng, eng2, sentence, pos, chr_, anchor, anchor2, objective, vali
         feats = e.encode_tokens(tok, ln, norm, base, (groups * per, per))
         _, _, loss = e.score(feats, a.expand(groups, -1).contiguous(), groups, per, objective, want_loss=True)
         out.append(loss)
-    return out
+    return out + [valid_d]
 
 
 def _prep(model, model_2, anchor_features, model_2_anchor_features, objective, V):
@@ -70,11 +72,16 @@ def _prep(model, model_2, anchor_features, model_2_anchor_features, objective, V
     return eng, eng2, Vt, a1, a2
 
 
+def _device_filter(eng, constrain) -> bool:
+    if constrain is True and not getattr(eng, "has_words", False):
+        raise LeafError("constrain=True needs engine.load_words(<the reference's NLTK word list>) first, or pass "
+                        "constrain=<callable(sentences, SS)>")
+    return constrain is True
+
+
 def _valid(constrain, sentence, pos, chr_):
     """constrain(sentences, SS) -> bool[1][len]: the reference's valid_sentence_batched (utils_attacks.py:110-143) needs
     NLTK corpora, so it enters as a caller-supplied callable, exactly as in attack_text_leaf."""
-    if constrain is True:
-        raise LeafError("constrain=True needs the reference's NLTK word list; pass constrain=<callable(sentences, SS)>")
     if not callable(constrain):
         return None
     SS = [generate_sentence(sentence, int(z), int(c)) for z, c in zip(pos.ravel(), chr_.ravel())]
@@ -86,6 +93,7 @@ def attack_text_charmer_inference(model, tokenizer, sentence, anchor_features, d
                                   model_2_anchor_features=None):
     """utils_attacks.py:451-580. One sentence at a time; `n` is the number of positions kept after the probe."""
     eng, eng2, Vt, a1, a2 = _prep(model, model_2, anchor_features, model_2_anchor_features, objective, V)
+    on_device = _device_filter(eng, constrain)
     nv = len(Vt)
     dist = 0
     for dist in range(k):
@@ -96,7 +104,7 @@ def attack_text_charmer_inference(model, tokenizer, sentence, anchor_features, d
         # ---- probe: a space at every position (:476-517); the last position is never scored ----
         pos1 = np.arange(n1, dtype=np.int32).reshape(1, n1)
         chr1 = np.full((1, n1), 32, dtype=np.int32)
-        l1, l1b = _score_list(eng, eng2, sentence, pos1, chr1, a1, a2, objective, _valid(constrain, sentence, pos1, chr1))
+        l1, l1b, _ = _score_list(eng, eng2, sentence, pos1, chr1, a1, a2, objective, _valid(constrain, sentence, pos1, chr1), on_device)
         kk = min(n, n1 - 1)
         top, _ = eng.topk(l1, kk, m=n1 - 1, score_b=l1b)                       # :519
         # ---- every character of V at the kept positions (:524-575) ----
@@ -105,13 +113,14 @@ def attack_text_charmer_inference(model, tokenizer, sentence, anchor_features, d
         if callable(constrain):                                               # the mask needs the strings: one extra D2H
             pos2 = np.repeat(top.cpu().numpy().reshape(kk, 1), nv, axis=1)
             valid2 = _valid(constrain, sentence, pos2, chr2)
-        l2, l2b = _score_list(eng, eng2, sentence, pos2, chr2, a1, a2, objective, valid2)
+        l2, l2b, vd = _score_list(eng, eng2, sentence, pos2, chr2, a1, a2, objective, valid2, on_device)
         win, _ = eng.topk(l2, 1, m=kk * nv - 1, score_b=l2b)                  # :575, last candidate never scored
-        res = torch.cat([top, win]).cpu().numpy()                             # the only device -> host read of the round
+        okd = torch.ones(1, dtype=torch.int32, device=win.device) if vd is None else vd.reshape(-1)[win.long()].to(torch.int32)
+        res = torch.cat([top, win, okd]).cpu().numpy()                        # the only device -> host read of the round
         eng.check_status()
-        g = int(res[-1])
+        g = int(res[-2])
         z, c = int(res[g // nv]), int(Vt[g % nv])
-        ok = True if valid2 is None else bool(valid2.ravel()[g])
+        ok = bool(res[-1])
         sentence = generate_sentence(sentence, z, c) if ok else sentence
         if debug:
             print(sentence)
@@ -125,16 +134,17 @@ def attack_text_bruteforce(model, tokenizer, sentence, anchor_features, device=N
     if objective not in ("l2", "dissim"):
         raise ValueError(f"attack_text_bruteforce supports objectives 'l2' and 'dissim', got {objective!r}")
     eng, _, Vt, a1, _ = _prep(model, None, anchor_features, None, objective, V)
+    on_device = _device_filter(eng, constrain)
     nv = len(Vt)
     n1 = 2 * len(sentence) + 1
     pos = np.repeat(np.arange(n1, dtype=np.int32).reshape(n1, 1), nv, axis=1)
     chr_ = np.tile(Vt.reshape(1, nv), (n1, 1))
     valid = _valid(constrain, sentence, pos, chr_)
-    loss, _ = _score_list(eng, None, sentence, pos, chr_, a1, None, objective, valid)
+    loss, _, vd = _score_list(eng, None, sentence, pos, chr_, a1, None, objective, valid, on_device)
     win, _ = eng.topk(loss, 1, m=n1 * nv - 1)                                # :447, last candidate never scored
     g = int(win.item())
     eng.check_status()
-    ok = True if valid is None else bool(valid.ravel()[g])
+    ok = True if vd is None else bool(vd.reshape(-1)[g].item())
     out = generate_sentence(sentence, int(pos.ravel()[g]), int(chr_.ravel()[g])) if ok else sentence
     if debug:
         print(out)

@@ -16,7 +16,7 @@ _lib = None
 
 def _deps_mtime():
     deps = [SRC] + [os.path.join(ROOT, "leaf_b200", "csrc", f) for f in
-                    ("k1_core.cuh", "k1_tables_host.h", "k1_tables.inc")]
+                    ("k1_core.cuh", "k1_tables_host.h", "k1_tables.inc", "constrain_core.cuh")]
     return max(os.path.getmtime(d) for d in deps)
 
 
@@ -52,3 +52,29 @@ def expand_tokenize(caps, n=0, pos=None, chr_=None, sel=None, valid=None, encodi
     ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
     flags = L.k1h_expand_tokenize(ptr(data), ptr(off), B, n, ptr(pos), ptr(chr_), ptr(sel), ptr(valid), ptr(tok), ptr(ln))
     return tok, ln, flags
+
+
+def load_words(words, abbrev=()):
+    L = lib()
+    def pack(ws):
+        blobs = [w.encode("ascii") for w in ws if w.isascii()]
+        off = np.zeros(len(blobs) + 1, dtype=np.int32)
+        off[1:] = np.cumsum([len(b) for b in blobs])
+        return np.frombuffer(b"".join(blobs) + b"\0", dtype=np.uint8).copy(), off, len(blobs)
+    wb, wo, nw = pack(words)
+    ab, ao, na = pack(abbrev)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    L.cnh_load(p(wb), p(wo), nw, p(ab), p(ao), na)
+
+
+def constrain_counts(caps, n, pos, chr_, sel=None):
+    """Dictionary-word counts [B*n + B] (candidates, then the sentences) from the CPU-compiled filter core; flags."""
+    L = lib()
+    data, off = pack_captions(caps)
+    B = len(caps)
+    out = np.zeros(B * n + B, dtype=np.int32)
+    q = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+    pos, chr_, sel = q(pos, np.int32), q(chr_, np.int32), q(sel, np.int32)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    flags = L.cnh_counts(ptr(data), ptr(off), B, n, ptr(pos), ptr(chr_), ptr(sel), ptr(out))
+    return out, flags

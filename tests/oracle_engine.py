@@ -14,6 +14,17 @@ class OracleEngine:
         self.device = torch.device("cpu")
         self.embed_dim = int(sd["text_projection"].shape[1])
         self.encoded_rows = 0
+        self.has_words = False
+
+    def load_words(self, words, abbrev=()):
+        H.load_words(words, abbrev)
+        self.has_words = True
+
+    def constrain_mask(self, caps, off, B, n, pos, chr_, sel=None, want_counts=False):
+        a = lambda t: None if t is None else t.numpy()
+        counts, _ = H.constrain_counts(caps, n, a(pos), a(chr_), a(sel))
+        valid = (counts[:B * n].reshape(B, n) < counts[B * n:].reshape(B, 1)).astype(np.uint8)
+        return torch.from_numpy(valid)
 
     def reserve(self, n):
         pass

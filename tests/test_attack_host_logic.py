@@ -88,6 +88,31 @@ def test_constraint_mask_replaces_candidates_by_the_current_sentence():
     assert adv == c["captions"]                       # utils_attacks.py:325/:364: invalid -> the sentence itself
 
 
+def test_device_constraint_reproduces_the_oracle_attack_with_the_filter():
+    """constrain=True (masks from the filter core, no candidate strings on the host) against the oracle attack loop driven
+    by the oracle's restatement of valid_sentence_batched, k = 2 so that round 2 compares against round 1's winners."""
+    from oracle import leaf_oracle as O
+    from oracle import nltk_restate as N
+    from tests.test_constrain_cpu import ABBREV, _word_list
+    g, z, cfg, sd = _setup()
+    words = _word_list()
+    eng = OracleEngine(sd, cfg.heads)
+    eng.load_words(words, ABBREV)
+    W, A = frozenset(words), frozenset(ABBREV)
+    caps = synth.make_captions(5, seed=9)
+    anchor = torch.from_numpy(z["anchor_0"])[:5].clone()
+    otok = O.OracleTokenizer()
+    enc = lambda t, normalize: O.encode_text(sd, t, cfg.heads, normalize=normalize)
+    np.random.seed(5)
+    want_f, want = O.attack_text_leaf_oracle(enc, otok, caps, anchor, n=30, k=2,
+                                             valid_fn=lambda s, SS: N.valid_sentence_batched(s, SS, W, A))
+    np.random.seed(5)
+    feats, adv = attack_text_leaf(eng, None, caps, anchor.clone(), "cpu", n=30, k=2, constrain=True)
+    assert adv == want
+    assert np.abs(feats.numpy() - want_f.numpy()).max() < 1e-4
+    assert adv != caps
+
+
 def test_cross_shard_argmax_single_process():
     v, i = torch.tensor([1.0, 2.0]), torch.tensor([3, 4])
     assert D.cross_shard_argmax(v, i) == (v, i)

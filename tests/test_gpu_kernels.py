@@ -217,3 +217,51 @@ def test_k1_matches_cpu_compiled_core_at_full_size(eng):
     htok, hln, _ = H.expand_tokenize(caps, n, pos, chr_)
     assert (tok == htok).all() and (ln == hln).all()
     eng._status.zero_()
+
+
+def test_constrain_mask_matches_oracle(eng):
+    """leaf_constrain_mask (thread per sentence) against the oracle's restatement of valid_sentence_batched
+    (utils_attacks.py:110-143 over nltk.word_tokenize, oracle/nltk_restate.py), both phases' candidate forms, and the
+    CPU-compiled core at the full attack size."""
+    from leaf_b200 import synth
+    from oracle import leaf_oracle as O
+    from oracle import nltk_restate as N
+    from tests import k1_harness as H
+    from tests.test_constrain_cpu import ABBREV, _texts, _word_list
+    words = _word_list()
+    eng.load_words(words, ABBREV)
+    H.load_words(words, ABBREV)
+    W, A = frozenset(words), frozenset(ABBREV)
+    V = np.asarray(synth.V_DEFAULT, dtype=np.int32)
+    caps = synth.make_captions(10, seed=3) + ["a photo of a cat's toy, isn't it? yes. the dog (brown) can't stop.",
+                                               'he said "hello there." then left -- cannot go', "mr. smith's dog & cat: a,b"] \
+        + [t for t in _texts(7, 40) if t.isascii() and len(t) > 0][:20]
+    B, n = len(caps), 50
+    rs = np.random.RandomState(1)
+    pos = np.stack([rs.randint(0, 2 * len(S) + 1, size=n) for S in caps]).astype(np.int32)
+    chr_ = V[rs.randint(0, len(V), size=(B, n))]
+    d, o = eng.upload_captions(caps)
+    pos_d, chr_d = torch.from_numpy(pos).cuda(), torch.from_numpy(chr_).cuda()
+    valid, counts = eng.constrain_mask(d, o, B, n, pos_d, chr_d, want_counts=True)
+    eng.check_status()
+    SS = [[O.edit_sentence(S, int(z), int(c)) for z, c in zip(pos[b], chr_[b])] for b, S in enumerate(caps)]
+    want = np.asarray(N.valid_sentence_batched(caps, SS, W, A), dtype=np.uint8)
+    assert np.array_equal(valid.cpu().numpy(), want)
+    assert counts[B * n:].cpu().tolist() == [N.count_dictionary_words(S, W, A) for S in caps]
+    sel = torch.from_numpy(rs.randint(0, n, size=B).astype(np.int32)).cuda()
+    valid2 = eng.constrain_mask(d, o, B, n, pos_d, chr_d, sel)
+    SS2 = [[O.edit_sentence(S, int(pos[b, int(sel[b])]), int(c)) for c in chr_[b]] for b, S in enumerate(caps)]
+    assert np.array_equal(valid2.cpu().numpy(), np.asarray(N.valid_sentence_batched(caps, SS2, W, A), dtype=np.uint8))
+    # the mask feeds leaf_expand_tokenize: invalid candidates come back as the unedited caption's row
+    tok, ln, base = eng.expand_tokenize(d, o, B, n, pos=pos_d, chr_=chr_d, valid=valid)
+    inv = (valid.view(-1) == 0).nonzero().flatten()
+    assert inv.numel() > 0 and torch.equal(tok[inv], tok[B * n + inv // n])
+    # full attack size against the CPU-compiled core
+    caps = synth.make_captions(128, seed=11)
+    B = 128
+    pos = np.stack([rs.randint(0, 2 * len(S) + 1, size=n) for S in caps]).astype(np.int32)
+    chr_ = V[rs.randint(0, len(V), size=(B, n))]
+    d, o = eng.upload_captions(caps)
+    _, counts = eng.constrain_mask(d, o, B, n, torch.from_numpy(pos).cuda(), torch.from_numpy(chr_).cuda(), want_counts=True)
+    hc, flags = H.constrain_counts(caps, n, pos, chr_)
+    assert flags == 0 and np.array_equal(counts.cpu().numpy(), hc)
