@@ -114,6 +114,11 @@ int leaf_expand_tokenize(leaf_handle_t h, const uint8_t* caps, const int32_t* ca
                          const int32_t* pos, const int32_t* chr, const int32_t* sel, const uint8_t* valid,
                          int32_t* tok_out, int32_t* len_out, int32_t* base_out, int32_t* status_out, void* stream);
 
+/* Which tokenizer leaf_expand_tokenize reproduces: 0 = open_clip's SimpleTokenizer (default; tokenizer.py:133-265),
+ * 1 = transformers' CLIPTokenizer as the reference's HF evaluation path wraps it (utils_attacks.py:67-71,
+ * eval_textfare.py:127): same BPE, no html.unescape, special tokens spelled <|startoftext|> / <|endoftext|>. */
+int leaf_set_tokenizer_mode(leaf_handle_t h, int32_t mode);
+
 /* ---- the `--constrain` filter on the device ---------------------------------------------------------
  * Replaces valid_sentence_batched (utils_attacks.py:110-143; applied at :321-325, :360-364, :478-481, :532-537):
  * valid[b,j] = len(W & set(word_tokenize(candidate.lower()))) < len(W & set(word_tokenize(sentence_b.lower()))).

@@ -80,6 +80,7 @@ struct leaf_engine {
   encode_tiled_fn encode_tiled = nullptr;
   // K1 tables
   bool bpe_loaded = false;
+  bool hf_tokenizer = false;          // leaf_set_tokenizer_mode
   std::vector<void*> table_allocs;
   K1Tables tables{};
   // --constrain filter: hash sets of the word list and of Punkt abbreviation types
@@ -456,7 +457,7 @@ extern "C" int leaf_expand_tokenize(leaf_handle_t e, const uint8_t* caps, const 
   if (!e->bpe_loaded) return fail(LEAF_ERR_STATE, "leaf_load_bpe has not been called");
   if (B <= 0 || n < 0) return fail(LEAF_ERR_INVALID, "B=%d n=%d", B, n);
   if (n > 0 && (!pos || !chr)) return fail(LEAF_ERR_INVALID, "pos/chr required when n > 0");
-  K1Args a{caps, cap_off, B, n, pos, chr, sel, valid, tok_out, len_out, base_out, status_out};
+  K1Args a{caps, cap_off, B, n, pos, chr, sel, valid, tok_out, len_out, base_out, status_out, e->hf_tokenizer ? 1 : 0};
   const long R = static_cast<long>(B) * (n > 0 ? n : 1) + (n > 0 ? B : 0);
   const int grid = static_cast<int>((R + K1_WARPS_PER_CTA - 1) / K1_WARPS_PER_CTA);
   k1_expand_tokenize_kernel<<<grid, K1_WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(e->tables, a);
@@ -979,5 +980,12 @@ extern "C" int leaf_constrain_mask(leaf_handle_t e, const uint8_t* caps, const i
   constrain_valid_kernel<<<(B * n + 255) / 256, 256, 0, st>>>(cnt, B, n, valid_out);
   e->launches += 2;
   CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+// 0 = open_clip SimpleTokenizer (default), 1 = transformers CLIPTokenizer (no html.unescape, <|startoftext|> spellings)
+extern "C" int leaf_set_tokenizer_mode(leaf_handle_t e, int32_t mode) {
+  if (!e || (mode != 0 && mode != 1)) return fail(LEAF_ERR_INVALID, "tokenizer mode %d", mode);
+  e->hf_tokenizer = mode == 1;
   return LEAF_OK;
 }

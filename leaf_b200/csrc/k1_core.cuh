@@ -220,7 +220,7 @@ K1_HD bool k1_match(const uint8_t* t, int n, int pos, const char* lit, int ll) {
 // ---- regex split of the cleaned text (tokenizer.py:160-163), first K1_MAX_PIECES pieces ------------------
 // piece_len gets 0x8000 | 0 for <start_of_text>, 0x8000 | 1 for <end_of_text> (ids straight from the cache,
 // tokenizer.py:159).
-K1_HD int k1_split(const K1Tables& T, const uint8_t* t, int n, uint16_t* piece_start, uint16_t* piece_len) {
+K1_HD int k1_split(const K1Tables& T, const uint8_t* t, int n, uint16_t* piece_start, uint16_t* piece_len, bool hf = false) {
   int np = 0, pos = 0;
   while (pos < n && np < K1_MAX_PIECES) {
     const uint8_t c = t[pos];
@@ -228,8 +228,9 @@ K1_HD int k1_split(const K1Tables& T, const uint8_t* t, int n, uint16_t* piece_s
     if (cl == 3) { ++pos; continue; }
     int len = 0;
     uint16_t special = 0;
-    if (c == '<' && k1_match(t, n, pos, "<start_of_text>", 15)) { len = 15; special = 0x8000; }
-    else if (c == '<' && k1_match(t, n, pos, "<end_of_text>", 13)) { len = 13; special = 0x8001; }
+    // transformers' CLIPTokenizer spells the two special tokens <|startoftext|> / <|endoftext|> (same lengths)
+    if (c == '<' && k1_match(t, n, pos, hf ? "<|startoftext|>" : "<start_of_text>", 15)) { len = 15; special = 0x8000; }
+    else if (c == '<' && k1_match(t, n, pos, hf ? "<|endoftext|>" : "<end_of_text>", 13)) { len = 13; special = 0x8001; }
     else if (c == '\'' && pos + 1 < n) {
       const uint8_t d = t[pos + 1];
       if (d == 's' || d == 't' || d == 'm' || d == 'd') len = 2;
@@ -253,7 +254,10 @@ K1_HD int k1_split(const K1Tables& T, const uint8_t* t, int n, uint16_t* piece_s
 
 // ---- everything a candidate needs before BPE (serial; lane 0 on the device) ------------------------------
 // src = caption bytes; do_edit selects the LEAF edit (z, c); returns flags.
-K1_HD int k1_prepare(const K1Tables& T, const uint8_t* src, int len, bool do_edit, int z, int c, K1Scratch& S) {
+// hf = true: the tokenizer of HF's CLIPTokenizer as the reference's eval path uses it (utils_attacks.py:67-71) - no
+// html.unescape, HF's special-token spellings; control characters other than \t \n \r (which its BasicTokenizer drops
+// instead of treating as white space) are outside the domain and flagged.
+K1_HD int k1_prepare(const K1Tables& T, const uint8_t* src, int len, bool do_edit, int z, int c, K1Scratch& S, bool hf = false) {
   int flags = 0;
   int n;
   if (do_edit) n = k1_apply_edit(src, len, z, c, S.buf_a);
@@ -261,8 +265,10 @@ K1_HD int k1_prepare(const K1Tables& T, const uint8_t* src, int len, bool do_edi
   bool amp = false;
   for (int i = 0; i < n; ++i) {
     if (S.buf_a[i] & 0x80) flags |= K1_FLAG_NON_ASCII;
+    if (hf && (S.buf_a[i] == 0x7f || (S.buf_a[i] < 0x20 && S.buf_a[i] != 9 && S.buf_a[i] != 10 && S.buf_a[i] != 13))) flags |= K1_FLAG_NON_ASCII;
     amp |= (S.buf_a[i] == '&');
   }
+  if (hf) amp = false;
   const uint8_t* cur = S.buf_a;
   if (amp) {                                               // html.unescape(html.unescape(text))
     n = k1_unescape(T, S.buf_a, n, S.buf_b, &flags);
@@ -270,7 +276,7 @@ K1_HD int k1_prepare(const K1Tables& T, const uint8_t* src, int len, bool do_edi
   }
   n = k1_clean(T, cur, n, S.buf_b);
   S.text_len = n;
-  S.n_pieces = k1_split(T, S.buf_b, n, S.piece_start, S.piece_len);
+  S.n_pieces = k1_split(T, S.buf_b, n, S.piece_start, S.piece_len, hf);
   return flags;
 }
 

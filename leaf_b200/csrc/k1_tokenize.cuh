@@ -27,6 +27,7 @@ struct K1Args {
   int32_t* len_out;
   int32_t* base_out;      // [R] index of the row holding the sample's unedited caption, -1 for those rows
   int32_t* status_out;
+  int hf_mode;            // 1: HF CLIPTokenizer semantics (leaf_set_tokenizer_mode)
 };
 
 __global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32) k1_expand_tokenize_kernel(const K1Tables T, const K1Args a) {
@@ -70,7 +71,7 @@ __global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32) k1_expand_tokenize_kern
       c = a.chr[r];
       if (z < 0 || z > 2 * len) { edit = false; flags |= K1_FLAG_TOO_LONG; }
     }
-    flags |= k1_prepare(T, s_src[w], len, edit, z, c, S);
+    flags |= k1_prepare(T, s_src[w], len, edit, z, c, S, a.hf_mode != 0);
     s_meta[w][0] = S.text_len;
     s_meta[w][1] = S.n_pieces;
   }

@@ -237,6 +237,47 @@ class LeafEngine:
                                      (16, "constraint filter buffer overflow")) if st & bit]
             raise LeafError("tokenizer kernel: " + "; ".join(what))
 
+    def set_tokenizer_mode(self, hf: bool):
+        """hf=True: token ids of transformers' CLIPTokenizer (the reference's HF evaluation path, utils_attacks.py:67-71)
+        instead of open_clip's SimpleTokenizer: no html.unescape, <|startoftext|> / <|endoftext|> spellings."""
+        check(self._lib.leaf_set_tokenizer_mode(self._h, 1 if hf else 0))
+        self.hf_tokenizer = bool(hf)
+
+    def tokenize_hf(self, texts, pad_id: int = 49407) -> torch.Tensor:
+        """tokenizer_wrapper.__call__ (utils_attacks.py:67-71): CLIPTokenizer(x, padding=True, truncation=True).input_ids -
+        int64 [N, longest row], padded with the tokenizer's pad id after the EOS. Needs set_tokenizer_mode(True)."""
+        if not getattr(self, "hf_tokenizer", False):
+            raise LeafError("tokenize_hf needs set_tokenizer_mode(True)")
+        if isinstance(texts, str):
+            texts = [texts]
+        d, o = self.upload_captions(texts)
+        tok, ln, _ = self.expand_tokenize(d, o, len(texts), 0)
+        self.check_status()
+        # row length = index of the LAST end-of-text + 1 (a literal <|endoftext|> inside the caption is an earlier one)
+        idx = torch.arange(CONTEXT_LENGTH, device=tok.device).view(1, -1)
+        n_tok = torch.where(tok == 49407, idx + 1, torch.zeros_like(idx)).max(dim=1).values
+        L = int(n_tok.max().item())
+        tok = tok[:, :L].long()
+        return torch.where(idx[:, :L] < n_tok.view(-1, 1), tok, torch.full_like(tok, pad_id))
+
+    def encode_hf_tokens(self, tok: torch.Tensor, eos_token_id: int = 49407, normalize: bool = False) -> torch.Tensor:
+        """HF CLIPTextModel(WithProjection) forward + pooling on HF-shaped rows [N, L <= 77] with any pad id: pooled at the
+        FIRST eos_token_id (modeling_clip.py's rule for eos_token_id != 2; for the legacy eos_token_id == 2 configs it is
+        argmax(ids), which is the same position for CLIP's vocabulary). Positions after the EOS are dead under the causal
+        mask, so the pad id never matters."""
+        tok = tok.to(self.device)
+        N, L = tok.shape
+        if L > CONTEXT_LENGTH:
+            raise LeafError(f"rows longer than the context length ({L} > {CONTEXT_LENGTH})")
+        is_eos = tok == eos_token_id
+        if not bool(is_eos.any(dim=1).all()):
+            raise LeafError("every row needs an EOS token")
+        ln = (is_eos.int().argmax(dim=1) + 1).to(torch.int32)
+        rows = torch.zeros((N, CONTEXT_LENGTH), dtype=torch.int32, device=self.device)
+        keep = torch.arange(L, device=self.device).view(1, L) < ln.view(-1, 1)
+        rows[:, :L] = torch.where(keep, tok.to(torch.int32), torch.zeros_like(tok, dtype=torch.int32))
+        return self.encode_tokens(rows, ln, normalize)
+
     def tokenize(self, texts, check=True) -> torch.Tensor:
         """SimpleTokenizer.__call__ (tokenizer.py:226-265): int64 [N,77] on the engine's device."""
         if isinstance(texts, str):

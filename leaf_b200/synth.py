@@ -69,6 +69,15 @@ def _pseudo_vocab(seed: int, size: int = 4096):
     return words
 
 
+def word_list(seed: int = 0, fraction: float = 0.5):
+    """Stand-in for nltk.corpus.words.words() on the synthetic captions (the real list is NLTK data): a deterministic
+    `fraction` of the pseudo-vocabulary make_captions(seed=...) draws from, so that roughly that share of a caption's
+    words counts as dictionary words for the --constrain filter."""
+    vocab = sorted(set(_pseudo_vocab(seed)))
+    rng = random.Random(7919 + seed)
+    return sorted(rng.sample(vocab, int(len(vocab) * fraction)))
+
+
 def make_captions(batch: int, seed: int = 0, kind: str = "typical"):
     """Printable-ASCII captions; no '&', '<', '_', ';' in the base text."""
     rng = random.Random(seed)

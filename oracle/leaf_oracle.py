@@ -109,7 +109,14 @@ class OracleTokenizer:
         r"""<start_of_text>|<end_of_text>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""",
         regex.IGNORECASE)                                              # tokenizer.py:160-163
 
-    def __init__(self, merges_path: str = _MERGES_BIN, context_length: int = CONTEXT_LENGTH):
+    # transformers CLIPTokenizer (models/clip/tokenization_clip.py): same BPE, but no html.unescape and the special
+    # tokens are spelled <|startoftext|> / <|endoftext|>
+    PAT_HF = regex.compile(
+        r"""<\|startoftext\|>|<\|endoftext\|>|'s|'t|'re|'ve|'m|'ll|'d|[\p{L}]+|[\p{N}]|[^\s\p{L}\p{N}]+""",
+        regex.IGNORECASE)
+
+    def __init__(self, merges_path: str = _MERGES_BIN, context_length: int = CONTEXT_LENGTH, hf: bool = False):
+        self.hf = hf
         pairs = np.fromfile(merges_path, dtype="<u4")
         assert pairs.shape[0] == 48894
         self.ranks = {(int(p) >> 16, int(p) & 0xFFFF): r for r, p in enumerate(pairs)}
@@ -149,13 +156,16 @@ class OracleTokenizer:
         return word
 
     def encode(self, text: str):
-        """tokenizer.py:213-219."""
+        """tokenizer.py:213-219. hf=True: CLIPTokenizer._tokenize without ftfy (BasicTokenizer: whitespace clean + lower,
+        which is all it does to printable ASCII), HF's pattern and special-token spellings."""
         out = []
-        for piece in self.PAT.findall(self.clean(text)):
-            if piece == "<start_of_text>":       # self.cache seeds the specials (tokenizer.py:159)
+        cleaned = " ".join(text.split()).strip().lower() if self.hf else self.clean(text)
+        sot, eot = ("<|startoftext|>", "<|endoftext|>") if self.hf else ("<start_of_text>", "<end_of_text>")
+        for piece in (self.PAT_HF if self.hf else self.PAT).findall(cleaned):
+            if piece == sot:                     # self.cache seeds the specials (tokenizer.py:159)
                 out.append(SOT)
                 continue
-            if piece == "<end_of_text>":
+            if piece == eot:
                 out.append(EOT)
                 continue
             got = self.cache.get(piece)
@@ -180,6 +190,20 @@ class OracleTokenizer:
                 toks[-1] = EOT
             res[i, :len(toks)] = toks
         return torch.from_numpy(res)
+
+    def hf_call(self, texts, pad_id: int = EOT, max_length: int = CONTEXT_LENGTH):
+        """tokenizer_wrapper.__call__ (utils_attacks.py:67-71): tokenizer(x, padding=True, truncation=True).input_ids as a
+        tensor - padded to the LONGEST row of the batch with the tokenizer's pad id, truncated to max_length with the
+        EOS kept."""
+        assert self.hf
+        rows = []
+        for t in ([texts] if isinstance(texts, str) else texts):
+            toks = [SOT] + self.encode(t) + [EOT]
+            if len(toks) > max_length:
+                toks = toks[:max_length - 1] + [EOT]
+            rows.append(toks)
+        L = max(len(r) for r in rows)
+        return torch.tensor([r + [pad_id] * (L - len(r)) for r in rows], dtype=torch.int64)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -231,6 +231,39 @@ def gen_eval_attacks():
     print("charmer cases", len(charmer), "bruteforce cases", len(brute))
 
 
+def gen_hf_tokenizer():
+    """transformers.CLIPTokenizer (slow, no ftfy) built from the reference's own BPE file, as eval_textfare.py's HF path
+    uses it through tokenizer_wrapper (utils_attacks.py:67-71): padding=True, truncation=True."""
+    import gzip
+    import tempfile
+    from open_clip.tokenizer import bytes_to_unicode, default_bpe
+    from transformers import CLIPTokenizer
+    merges = gzip.open(default_bpe()).read().decode("utf-8").split("\n")[1:49152 - 256 - 2 + 1]
+    vocab = list(bytes_to_unicode().values())
+    vocab = vocab + [v + "</w>" for v in vocab] + ["".join(m.split()) for m in merges] + ["<|startoftext|>", "<|endoftext|>"]
+    d = tempfile.mkdtemp()
+    json.dump({t: i for i, t in enumerate(vocab)}, open(os.path.join(d, "vocab.json"), "w"))
+    open(os.path.join(d, "merges.txt"), "w").write("#version: 0.2\n" + "\n".join(merges) + "\n")
+    tok = CLIPTokenizer(os.path.join(d, "vocab.json"), os.path.join(d, "merges.txt"), model_max_length=77)
+    rng = random.Random(13)
+    texts = ["a photo of a cat", "It's a DOG's life, isn't it?", "hello   world!!", "x" * 300, "a_b &amp; c &lt;", "3d 42 e.g. a cat.",
+             "x <|endoftext|> y", "<|startoftext|>a", "x <end_of_text> y", "", " ", "a\tb\nc", "don't'll", "#$%&'()*+", "a" * 90 + " " + "zq " * 80]
+    alpha = string.ascii_lowercase * 3 + string.ascii_uppercase + string.digits + "   '&;<_#x|" + string.punctuation
+    for _ in range(400):
+        texts.append("".join(rng.choice(alpha) for _ in range(rng.randint(1, 70))))
+    caps = synth.make_captions(16, seed=3, kind="typical") + synth.make_captions(3, seed=3, kind="dense-77")
+    for S in caps:
+        texts.append(S)
+        for _ in range(6):
+            texts.append(utils_attacks.generate_sentence(S, rng.randint(0, 2 * len(S)), rng.randrange(len(V)), V, 1, alternative=-1))
+    enc = [[t, tok(t).input_ids] for t in texts]
+    batches = [texts[:7], caps[:5], [caps[0], caps[17]], ["a", "x" * 300]]
+    wrapped = [[b, utils_attacks.tokenizer_wrapper(tok)(b).tolist()] for b in batches]
+    json.dump({"pad_id": tok.pad_token_id, "eos_id": tok.eos_token_id, "encode": enc, "wrapped": wrapped},
+              open(os.path.join(OUT, "hf_tokenizer_golden.json"), "w"))
+    print("hf tokenizer strings", len(enc), "pad", tok.pad_token_id)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -239,3 +272,4 @@ if __name__ == "__main__":
     gen_tower()
     gen_attack()
     gen_eval_attacks()
+    gen_hf_tokenizer()

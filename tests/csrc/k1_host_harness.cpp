@@ -12,6 +12,9 @@
 using namespace leaf;
 
 static std::vector<uint64_t> g_tab;
+static bool g_hf = false;
+
+extern "C" int k1h_set_mode(int hf) { g_hf = hf != 0; return 0; }
 
 extern "C" int k1h_load(const uint32_t* merge_pairs, int n) {
   g_tab = k1_build_merge_table(merge_pairs, n);
@@ -39,7 +42,7 @@ extern "C" int k1h_expand_tokenize(const uint8_t* caps, const int32_t* cap_off, 
       z = sel ? pos[bb * n + sel[bb]] : pos[r];
       c = chr[r];
     }
-    flags |= k1_prepare(T, src, len, edit, z, c, S);
+    flags |= k1_prepare(T, src, len, edit, z, c, S, g_hf);
     for (int p = 0; p < S.n_pieces; ++p) k1_encode_piece(T, S, p);
     len_out[r] = k1_emit_row(S, tok_out + (size_t)r * K1_CTX);
   }

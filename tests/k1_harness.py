@@ -39,9 +39,10 @@ def pack_captions(caps, encoding="ascii"):
     return data, off
 
 
-def expand_tokenize(caps, n=0, pos=None, chr_=None, sel=None, valid=None, encoding="ascii"):
+def expand_tokenize(caps, n=0, pos=None, chr_=None, sel=None, valid=None, encoding="ascii", hf=False):
     """Returns (tokens [R,77] int32, lengths [R] int32, flags)."""
     L = lib()
+    L.k1h_set_mode(1 if hf else 0)
     data, off = pack_captions(caps, encoding)
     B = len(caps)
     R = B * max(n, 1)

@@ -265,3 +265,32 @@ def test_constrain_mask_matches_oracle(eng):
     _, counts = eng.constrain_mask(d, o, B, n, torch.from_numpy(pos).cuda(), torch.from_numpy(chr_).cuda(), want_counts=True)
     hc, flags = H.constrain_counts(caps, n, pos, chr_)
     assert flags == 0 and np.array_equal(counts.cpu().numpy(), hc)
+
+
+def test_hf_tokenizer_mode_and_hf_shaped_rows(eng, golden_dir):
+    """HF wire compatibility: token ids of transformers' CLIPTokenizer, the tokenizer_wrapper layout
+    (padded to the longest row with the pad id), and the forward on such rows with HF's first-EOS pooling."""
+    g = json.load(open(os.path.join(golden_dir, "hf_tokenizer_golden.json")))
+    eng.set_tokenizer_mode(True)
+    try:
+        for batch, rows in g["wrapped"]:
+            got = eng.tokenize_hf(batch, pad_id=g["pad_id"])
+            assert got.cpu().tolist() == rows
+        texts = [s for s, _ in g["encode"] if len(s) <= 1000][:300]
+        tok = eng.tokenize(texts)
+        for i, (s, ids) in enumerate([(s, ids) for s, ids in g["encode"] if len(s) <= 1000][:300]):
+            want = ids if len(ids) <= 77 else ids[:76] + [49407]
+            assert tok[i, :len(want)].cpu().tolist() == want, s
+        # forward on HF-shaped rows == forward on the engine's own 77-slot rows
+        batch = g["wrapped"][1][0]
+        hf_rows = eng.tokenize_hf(batch, pad_id=g["pad_id"])
+        assert hf_rows.shape[1] < 77
+        f_hf = eng.encode_hf_tokens(hf_rows, eos_token_id=g["eos_id"])
+        f = eng.encode_tokens(eng.tokenize(batch))
+        assert torch.equal(f_hf, f)
+        f_pad0 = eng.encode_hf_tokens(torch.where(hf_rows == g["pad_id"], torch.zeros_like(hf_rows), hf_rows).where(
+            torch.arange(hf_rows.shape[1], device="cuda").view(1, -1) >= (hf_rows == g["eos_id"]).int().argmax(1, keepdim=True) + 1,
+            hf_rows), eos_token_id=g["eos_id"])
+        assert torch.equal(f_pad0, f)                                   # the pad id after the EOS never matters
+    finally:
+        eng.set_tokenizer_mode(False)

@@ -120,3 +120,18 @@ def test_random_fuzz_vs_oracle():
     assert ok.mean() > 0.9
     bad = np.nonzero((tok != want).any(axis=1) & ok)[0]
     assert len(bad) == 0, [(texts[i], tok[i][:10].tolist(), want[i][:10].tolist()) for i in bad[:5]]
+
+
+def test_hf_mode_matches_transformers(golden_dir):
+    """The K1 core in HF mode (leaf_set_tokenizer_mode 1) against transformers' CLIPTokenizer."""
+    import json
+    g = json.load(open(os.path.join(golden_dir, "hf_tokenizer_golden.json")))
+    texts = [s for s, _ in g["encode"] if len(s) <= 1000]
+    tok, ln, flags = H.expand_tokenize(texts, hf=True)
+    assert flags == 0
+    for i, (s, ids) in enumerate((s, ids) for s, ids in g["encode"] if len(s) <= 1000):
+        want = ids if len(ids) <= 77 else ids[:76] + [49407]
+        assert tok[i, :len(want)].tolist() == want, s
+        assert not tok[i, len(want):].any()
+        assert ln[i] == want.index(49407) + 1                    # pooled position: the FIRST EOS (argmax)
+    H.expand_tokenize(["x"])                                  # back to the default mode for the other tests
