@@ -318,3 +318,31 @@ def test_eval_attacks_golden(golden_dir):
             agree += int(adv == c["adv"])
     assert total >= 6, total
     assert agree == total, (agree, total)
+
+
+def test_bigg_width_tower_and_rho_sweep():
+    """BASELINE config 5's shape in small: the ViT-bigG-14 text-tower WIDTH (1280, 20 heads; a 3-layer copy so the fp32
+    oracle finishes in seconds) against the oracle, and attack_text_leaf over rho = 10 .. 200 (rho = 200 > 96 draws
+    characters WITH replacement, utils_attacks.py:236): winners are the argmax of their own phase and one edit away."""
+    from leaf_b200 import attack_text_leaf, synth
+    from leaf_b200.tower import LeafTextTower
+    from oracle import leaf_oracle as O
+    cfg = synth.TowerCfg("ViT-bigG-14-3L", 1280, 3, 20, 1280)
+    tower = LeafTextTower.random(cfg, seed=5)
+    caps = synth.make_captions(4, seed=6) + synth.make_captions(1, seed=6, kind="dense-77")
+    tok = tower.tokenizer(caps)
+    sd = {k: v.cpu() for k, v in tower.open_clip_state_dict().items()}
+    want = O.encode_text(sd, tok.cpu(), cfg.heads)
+    f = tower.encode_text(tok)
+    assert _cos(f.cpu(), want).min() >= COS_MIN
+    anchor = (f + 0.05 * torch.randn_like(f)).contiguous()
+    for rho in (10, 20, 50, 100, 200):
+        np.random.seed(rho)
+        feats, adv = attack_text_leaf(tower, None, caps, anchor.clone(), "cuda", objective="l2", n=rho, k=1)
+        again = tower.encode_text(tower.tokenizer(adv))
+        assert torch.equal(again, feats)                       # the returned features are the winners' own
+        for a, c in zip(adv, caps):
+            assert abs(len(a) - len(c)) <= 1
+        loss_adv = ((feats - anchor) ** 2).sum(-1)
+        loss_clean = ((f - anchor) ** 2).sum(-1)
+        assert bool((loss_adv >= loss_clean * (1 - LOSS_RTOL)).all()) or rho < 20

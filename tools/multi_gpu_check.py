@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Multi-GPU parity of the sharded attack modes over NCCL: under torchrun, every rank runs the unsharded
+attack on the whole batch AND the sample- / candidate-sharded attacks; all three must select the same winners (bit-equal
+scores: every candidate row is computed by the same kernels whatever rank holds it). BASELINE config 4's shape in small:
+ViT-g-14 text tower width (a shallow copy), k = 2, candidate-sharded.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from leaf_b200 import attack_text_leaf, synth  # noqa: E402
+from leaf_b200.fare import FareTrainer  # noqa: E402
+from leaf_b200.tower import LeafTextTower  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+cfg = synth.TowerCfg("ViT-g-14-4L", 1024, 4, 16, 1024)
+sd = synth.random_tower_state_dict(cfg, seed=0, exact_numpy=False, device="cpu")
+tower = LeafTextTower(sd, heads=cfg.heads, device=dev)
+frozen = LeafTextTower(synth.perturbed_copy(sd, seed=1, std=1e-2), heads=cfg.heads, device=dev)
+B, n, k = 12, 50, 2
+caps = synth.make_captions(B, seed=5)
+anchor = frozen.encode_text(frozen.tokenizer(caps))
+res = {}
+for mode in (None, "samples", "candidates"):
+    np.random.seed(7)
+    feats, adv = attack_text_leaf(tower, None, caps, anchor.clone(), dev, objective="l2", n=n, k=k, shard=mode)
+    res[mode] = (feats, adv)
+ok = True
+for mode in ("samples", "candidates"):
+    same = res[mode][1] == res[None][1]
+    close = torch.equal(res[mode][0], res[None][0])
+    print(f"rank {rank}: shard={mode}: winners equal {same}, features bit-equal {close}", flush=True)
+    ok &= same and close
+# data-parallel FARE step: each rank its own micro-batch, gradients averaged by ONE all-reduce of the flat buffer;
+# afterwards the parameters must be identical on every rank
+tr = FareTrainer(tower, frozen, rho=20, k_adv=1, lr=1e-4)
+np.random.seed(100 + rank)
+loss, _ = tr.step(synth.make_captions(8, seed=50 + rank))
+flat = tower.flat_params.clone()
+ref = flat.clone()
+dist.broadcast(ref, src=0)
+same_params = torch.equal(flat, ref)
+print(f"rank {rank}: FARE step loss {loss.item():.4f}, parameters identical across ranks after the update: {same_params}", flush=True)
+ok &= same_params
+t = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTI_GPU_CHECK", "PASS" if t.item() == 1 else "FAIL", f"world={world}", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if t.item() == 1 else 1)
