@@ -12,6 +12,8 @@ gradients one memset (leaf_b200/fare.py).
 """
 from __future__ import annotations
 
+import re
+
 import torch
 
 from . import synth
@@ -42,9 +44,27 @@ class _EncodeTextTrain(torch.autograd.Function):
         return (None, None) + (None,) * len(grads)
 
 
+_TEXT_KEYS = re.compile(r"^(text\.)?(token_embedding\.weight|positional_embedding|ln_final\.(weight|bias)|text_projection(\.weight)?|"
+                        r"transformer\.resblocks\.\d+\.(ln_1|ln_2|attn\.out_proj|mlp\.c_fc|mlp\.c_proj)\.(weight|bias)|"
+                        r"transformer\.resblocks\.\d+\.attn\.in_proj_(weight|bias))$")
+
+
+def text_tower_state_dict(state_dict: dict) -> dict:
+    """The text-tower entries of an open_clip CLIP / CustomTextCLIP state dict: everything under
+    `visual.`, `logit_scale`, the attention-mask buffer etc. is dropped; a `text.` prefix is removed."""
+    out = {}
+    for k, v in state_dict.items():
+        if _TEXT_KEYS.match(k):
+            out[k[5:] if k.startswith("text.") else k] = v
+    return out
+
+
 class LeafTextTower(torch.nn.Module):
     def __init__(self, state_dict: dict, heads: int, quick_gelu: bool = False, device="cuda"):
         super().__init__()
+        state_dict = text_tower_state_dict(state_dict)
+        if "token_embedding.weight" not in state_dict:
+            raise ValueError("LeafTextTower needs an open_clip text tower state dict (token_embedding.weight, ...)")
         items = sorted(state_dict.items(), key=lambda kv: 0 if no_weight_decay(kv[0], kv[1].dim()) else 1)   # stable
         sizes = [(v.numel() + 3) // 4 * 4 for _, v in items]                     # 16-byte aligned slices
         self._flat = torch.zeros(sum(sizes), dtype=torch.float32, device=device)
