@@ -306,7 +306,7 @@ def run_ours(a):
     torch.cuda.synchronize()
     gemm_ms, gemm_launches = eng.gemm_time_ms()
     insitu = {name: round(eng.class_time_ms(i)[0], 3) for i, name in enumerate(("gemm", "layernorm", "attention", "pack_embed"))}
-    for epi, name in enumerate(("gemm_qkv_bf16", "gemm_fc1_bf16_act", "gemm_out_fc2_residual", "gemm_proj_f32")):
+    for epi, name in enumerate(("gemm_qkv_bf16", "gemm_fc1_bf16_act", "gemm_out_fc2_residual", "gemm_proj_f32", "gemm_fc2_residual")):
         ms_epi, n_epi = eng.class_time_ms(4 + epi)
         if n_epi:
             insitu[name] = [round(ms_epi, 3), n_epi]
@@ -314,7 +314,10 @@ def run_ours(a):
     lens = torch.cat([r[0] for r in rec]).double().cpu().numpy()
     rows_exec = sum(r[1] for r in rec)                                        # packed rows the GEMMs really processed
     W, L, E = cfg.width, cfg.layers, cfg.embed_dim
-    gemm_flops = rows_exec * L * 24.0 * W * W + 2.0 * len(rec) * (B * n + B) * 2.0 * W * E   # executed by the GEMM launches
+    # executed by the GEMM launches: every packed row through L-1 whole layers and the final layer's QKV projection; the
+    # final layer's out-proj + MLP and the text projection see one (pooled EOS) row per sequence
+    seqs = len(rec) * (B * n + B)
+    gemm_flops = rows_exec * ((L - 1) * 24.0 + 6.0) * W * W + seqs * (18.0 * W * W + 2.0 * W * E)
     gemm_flops_credit = float((L * 24.0 * lens * W * W + 2.0 * W * E).sum())   # GEMM share of F(t), SURVEY.md 8d
     alg_flops = float(sum(cfg.flops_for_length(int(x)) for x in lens))
     peak_tf, peak_gbs, peak_src = peaks()

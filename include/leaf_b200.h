@@ -198,12 +198,15 @@ int leaf_test_layernorm(leaf_handle_t h, const float* x, int32_t rows, const flo
 /* out[rows,W] (bf16) = causal attention over packed qkv[rows,3W] (bf16); meta [N,4] int32 = {own_row, t, p, base_row}
  * per sequence (positions [p,t) are rows own_row.., keys/values of [0,p) are rows base_row..). */
 int leaf_test_attention(leaf_handle_t h, const void* qkv, const int32_t* meta, int32_t N, void* out, void* stream);
+/* leaf_encode computes the final layer's out-proj / LayerNorm / MLP on the pooled EOS row of every sequence only (the
+ * one row transformer.py:661 reads); on by default, results are bit-identical either way. on = 0 computes every row. */
+int leaf_set_prune_last(leaf_handle_t h, int32_t on);
 /* Number of kernels the engine has launched since the last call with reset != 0. */
 int64_t leaf_launch_count(leaf_handle_t h, int32_t reset);
 /* Packed-row count (sum of len) of the last leaf_encode; synchronises the device. */
 int64_t leaf_last_rows(leaf_handle_t h);
 /* Accumulated device time (ms) of the launches of class `which` (0 = GEMM, 1 = LayerNorm, 2 = attention, 3 = row
- * packing + embedding, 4 + e = the GEMM launches with epilogue e) between CUDA events recorded on the launching stream, since timing was last enabled with
+ * packing + embedding, 4 + e = the GEMM launches with epilogue e, 8 = the residual GEMMs with K > N, i.e. fc2) between CUDA events recorded on the launching stream, since timing was last enabled with
  * leaf_set_timing(h, 1). Synchronises on the recorded events. */
 int leaf_set_timing(leaf_handle_t h, int32_t on);
 double leaf_timing_ms(leaf_handle_t h, int32_t which, int32_t* launches);

@@ -104,6 +104,9 @@ struct leaf_engine {
   __nv_bfloat16* h = nullptr;         // [rows_cap, W]  LN output / attention output
   __nv_bfloat16* big = nullptr;       // [rows_cap, 4W] qkv (3W) or MLP hidden (4W)
   __nv_bfloat16* pooled = nullptr;    // [max_seqs, W]
+  float* xc = nullptr;                // [max_seqs, W] fp32 residual rows of the pooled positions (final layer, compact)
+  int* first_of = nullptr;            // [max_seqs] sequence whose rows stand for sequence i
+  bool prune_last = true;             // final layer: out-proj + MLP on the pooled rows only
   int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr, *dup_of = nullptr;
   int4* meta = nullptr;
   // bookkeeping
@@ -111,8 +114,8 @@ struct leaf_engine {
   bool timing = false;
   struct Span { cudaEvent_t a, b; int cat; };
   std::vector<Span> spans;            // cat: 0 GEMM, 1 LayerNorm, 2 attention, 3 everything else of the encode
-  double span_ms[8] = {0};         // 4 + epi: the GEMM launches of one epilogue kind (also counted in class 0)
-  int span_n[8] = {0};
+  double span_ms[9] = {0};         // 4 + epi: the GEMM launches of one epilogue kind (also counted in class 0);
+  int span_n[9] = {0};             // 8: the residual GEMMs with K > N (fc2), counted in class 6 as well
   std::vector<cudaEvent_t> event_pool;
   std::map<std::tuple<const void*, long, long, int>, CUtensorMap> tmaps;
 };
@@ -176,7 +179,7 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act;
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
   const long tiles = static_cast<long>(m_tiles) * n_tiles;
-  TimedSpan span(e, 4 + epi, st);
+  TimedSpan span(e, (epi == EPI_F32_RESIDUAL && K > N) ? 8 : 4 + epi, st);
   const int pairs_max = e->sm_count / 2;
   const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
   cudaLaunchConfig_t cfg{};
@@ -237,7 +240,8 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
 }
 
 static void free_workspace(leaf_engine* e) {
-  cudaFree(e->x); cudaFree(e->h); cudaFree(e->big); cudaFree(e->pooled);
+  cudaFree(e->x); cudaFree(e->h); cudaFree(e->big); cudaFree(e->pooled); cudaFree(e->xc); cudaFree(e->first_of);
+  e->xc = nullptr; e->first_of = nullptr;
   cudaFree(e->cu); cudaFree(e->eos_row); cudaFree(e->total_rows); cudaFree(e->pfx); cudaFree(e->own_len); cudaFree(e->dup_of); cudaFree(e->meta);
   e->x = nullptr; e->h = nullptr; e->big = nullptr; e->pooled = nullptr;
   e->cu = e->eos_row = e->total_rows = e->pfx = e->own_len = e->dup_of = nullptr;
@@ -437,6 +441,8 @@ extern "C" int leaf_reserve(leaf_handle_t e, int32_t max_seqs) {
   CK(cudaMalloc(&e->h, rows * W * 2));
   CK(cudaMalloc(&e->big, rows * 4 * W * 2));
   CK(cudaMalloc(&e->pooled, (static_cast<size_t>(max_seqs) + 128) * W * 2));
+  CK(cudaMalloc(&e->xc, (static_cast<size_t>(max_seqs) + 128) * W * 4));
+  CK(cudaMalloc(&e->first_of, static_cast<size_t>(max_seqs) * 4));
   CK(cudaMalloc(&e->cu, (static_cast<size_t>(max_seqs) + 1) * 4));
   CK(cudaMalloc(&e->eos_row, static_cast<size_t>(max_seqs) * 4));
   CK(cudaMalloc(&e->pfx, static_cast<size_t>(max_seqs) * 4));
@@ -509,7 +515,7 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
   }
   prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, base, dup, N, e->pfx, e->own_len);
   scan_lengths_kernel<<<1, 1024, 0, st>>>(e->own_len, N, e->cu, e->total_rows);
-  meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(e->cu, e->pfx, base, dup, N, e->meta, e->eos_row);
+  meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(e->cu, e->pfx, base, dup, N, e->meta, e->eos_row, e->first_of);
   embed_kernel<<<N, 256, 0, st>>>(tok, e->meta, N, W, e->wp.token_embedding, e->wp.positional_embedding, e->x);
   e->launches += 4;
   }
@@ -519,18 +525,36 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
     const LayerW& w = e->lw[l];
     if ((rc = launch_layernorm(e, e->x, e->total_rows, rows_max, nullptr, p.ln1_w, p.ln1_b, e->h, st))) return rc;
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.qkv_w, w.qkv_b, e->big, 3 * W, rows_max, 3 * W, W, EPI_BF16, 0, e->total_rows, st))) return rc;
+    // Final layer: only the pooled EOS position of a sequence is read after it (transformer.py:661), so everything past
+    // the key/value projection runs on ONE row per sequence: attention writes the EOS query's output to h[seq], the
+    // residual rows are compacted into xc, and out-proj / LayerNorm / MLP see N rows instead of the packed row count.
+    const bool last = e->prune_last && l == e->cfg.layers - 1;
     {
       TimedSpan span(e, 2, st);
-      attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(e->big, e->meta, N, H, W, e->h);
+      attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(e->big, e->meta, N, H, W, e->h, last ? 1 : 0);
     }
     e->launches++;
     CK(cudaGetLastError());
+    if (last) {
+      {
+        TimedSpan span(e, 3, st);
+        gather_rows_f32_kernel<<<(N + 7) / 8, 256, 0, st>>>(e->x, e->eos_row, N, W, e->xc);
+        e->launches++;
+      }
+      if ((rc = launch_gemm(e, e->h, e->rows_cap, w.out_w, p.out_b, e->xc, W, N, W, W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+      if ((rc = launch_layernorm(e, e->xc, nullptr, N, nullptr, p.ln2_w, p.ln2_b, e->h, st))) return rc;
+      if ((rc = launch_gemm(e, e->h, e->rows_cap, w.fc1_w, p.fc1_b, e->big, 4 * W, N, 4 * W, W, EPI_BF16_ACT, e->cfg.activation, nullptr, st))) return rc;
+      if ((rc = launch_gemm(e, e->big, e->rows_cap, w.fc2_w, p.fc2_b, e->xc, W, N, W, 4 * W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+      break;
+    }
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.out_w, p.out_b, e->x, W, rows_max, W, W, EPI_F32_RESIDUAL, 0, e->total_rows, st))) return rc;
     if ((rc = launch_layernorm(e, e->x, e->total_rows, rows_max, nullptr, p.ln2_w, p.ln2_b, e->h, st))) return rc;
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.fc1_w, p.fc1_b, e->big, 4 * W, rows_max, 4 * W, W, EPI_BF16_ACT, e->cfg.activation, e->total_rows, st))) return rc;
     if ((rc = launch_gemm(e, e->big, e->rows_cap, w.fc2_w, p.fc2_b, e->x, W, rows_max, W, 4 * W, EPI_F32_RESIDUAL, 0, e->total_rows, st))) return rc;
   }
-  if ((rc = launch_layernorm(e, e->x, nullptr, N, e->eos_row, e->wp.lnf_w, e->wp.lnf_b, e->pooled, st))) return rc;
+  if (e->prune_last) rc = launch_layernorm(e, e->xc, nullptr, N, e->first_of, e->wp.lnf_w, e->wp.lnf_b, e->pooled, st);
+  else rc = launch_layernorm(e, e->x, nullptr, N, e->eos_row, e->wp.lnf_w, e->wp.lnf_b, e->pooled, st);
+  if (rc) return rc;
   if ((rc = launch_gemm(e, e->pooled, e->max_seqs + 128, e->proj_w, nullptr, feat_out, E, N, E, W, EPI_F32, 0, nullptr, st))) return rc;
   if (normalize) {
     l2_normalize_kernel<<<(N + 7) / 8, 256, 0, st>>>(feat_out, N, E);
@@ -589,6 +613,12 @@ extern "C" int leaf_test_attention(leaf_handle_t e, const void* qkv, const int32
   return LEAF_OK;
 }
 
+extern "C" int leaf_set_prune_last(leaf_handle_t e, int32_t on) {
+  if (!e) return fail(LEAF_ERR_INVALID, "null handle");
+  e->prune_last = on != 0;
+  return LEAF_OK;
+}
+
 extern "C" int64_t leaf_launch_count(leaf_handle_t e, int32_t reset) {
   if (!e) return 0;
   const int64_t v = e->launches;
@@ -610,13 +640,13 @@ extern "C" int leaf_set_timing(leaf_handle_t e, int32_t on) {
   if (e->timing) {                               // a new measurement starts from zero
     int32_t dummy;
     leaf_timing_ms(e, 0, &dummy);
-    for (int i = 0; i < 8; ++i) { e->span_ms[i] = 0; e->span_n[i] = 0; }
+    for (int i = 0; i < 9; ++i) { e->span_ms[i] = 0; e->span_n[i] = 0; }
   }
   return LEAF_OK;
 }
 
 extern "C" double leaf_timing_ms(leaf_handle_t e, int32_t which, int32_t* launches) {
-  if (!e || which < 0 || which > 7) return 0.0;
+  if (!e || which < 0 || which > 8) return 0.0;
   if (!e->spans.empty()) {                       // fold the recorded spans into the per-category totals
     for (auto& sp : e->spans) {
       cudaEventSynchronize(sp.b);
@@ -624,6 +654,7 @@ extern "C" double leaf_timing_ms(leaf_handle_t e, int32_t which, int32_t* launch
       if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
         e->span_ms[sp.cat] += ms; e->span_n[sp.cat]++;
         if (sp.cat >= 4) { e->span_ms[0] += ms; e->span_n[0]++; }
+        if (sp.cat == 8) { e->span_ms[4 + EPI_F32_RESIDUAL] += ms; e->span_n[4 + EPI_F32_RESIDUAL]++; }
       }
       e->event_pool.push_back(sp.a);
       e->event_pool.push_back(sp.b);

@@ -120,9 +120,11 @@ __global__ void __launch_bounds__(256) dedup_kernel(const int* __restrict__ tok,
   if (lane == 0) dup_of[i] = found;
 }
 
-// meta[i] = {own_row, t, p, base_row}; eos_row[i] = last own row (of the first occurrence for a duplicate)
+// meta[i] = {own_row, t, p, base_row}; eos_row[i] = last own row (of the first occurrence for a duplicate);
+// first_of[i] = the sequence whose rows stand for sequence i (itself unless it is a duplicate)
 __global__ void meta_kernel(const int* __restrict__ cu, const int* __restrict__ pfx, const int* __restrict__ base,
-                            const int* __restrict__ dup_of, int N, int4* __restrict__ meta, int* __restrict__ eos_row) {
+                            const int* __restrict__ dup_of, int N, int4* __restrict__ meta, int* __restrict__ eos_row,
+                            int* __restrict__ first_of = nullptr) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int own = cu[i], n_own = cu[i + 1] - own, p = pfx[i];
@@ -130,6 +132,7 @@ __global__ void meta_kernel(const int* __restrict__ cu, const int* __restrict__ 
   meta[i] = make_int4(own, p + n_own, p, cu[b]);
   const int d = (dup_of && dup_of[i] >= 0) ? dup_of[i] : i;
   eos_row[i] = cu[d + 1] - 1;
+  if (first_of) first_of[i] = d;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -330,7 +333,8 @@ __device__ __forceinline__ void attention_tile(const __nv_bfloat16* __restrict__
 
 __global__ void __launch_bounds__(ATT_WARPS * 32, 4) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                        const int4* __restrict__ meta, int n_seq, int heads,
-                                                                       int W, __nv_bfloat16* __restrict__ out) {
+                                                                       int W, __nv_bfloat16* __restrict__ out,
+                                                                       int last_only = 0) {
   const int pair = blockIdx.x * ATT_WARPS + (threadIdx.x >> 5);
   if (pair >= n_seq * heads) return;
   const int seq = pair / heads, head = pair - seq * heads;
@@ -338,11 +342,14 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 4) attention_kernel(const __nv
   const int4 mt = __ldg(meta + seq);
   const int own_row = mt.x, t = mt.y, p = mt.z, base_row = mt.w;
   const int nq = t - p;
+  if (nq <= 0) return;                                       // duplicate of an earlier sequence: owns no rows
   const size_t ld = static_cast<size_t>(3) * W;
   const __nv_bfloat16* qbase = qkv + head * 64 + c * 8;
   const __nv_bfloat16* kbase = qbase + W;
   const __nv_bfloat16* vbase = qbase + 2 * W;
-  for (int q0 = 0; q0 < nq; q0 += 16) {
+  // last_only (final layer): only the pooled EOS position feeds the output (transformer.py:661), so only the query
+  // tile that holds it is computed and its row is written to out[seq] (one compact row per sequence).
+  for (int q0 = last_only ? ((nq - 1) & ~15) : 0; q0 < nq; q0 += 16) {
     // ---- Q fragments: rows q0+g and q0+g+8, two 32-wide d blocks, 8 contiguous bf16 per lane and block ----
     const int qi0 = min(q0 + g, nq - 1), qi1 = min(q0 + g + 8, nq - 1);
     uint32_t qf[2][8];
@@ -377,10 +384,25 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 4) attention_kernel(const __nv
       w1.z = pack_bf16x2(o[b * 4 + 2][2] * inv1, o[b * 4 + 2][3] * inv1);
       w1.w = pack_bf16x2(o[b * 4 + 3][2] * inv1, o[b * 4 + 3][3] * inv1);
       __nv_bfloat16* ob = out + head * 64 + b * 32 + c * 8;
-      if (q0 + g < nq) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(own_row + q0 + g) * W) = w0;
-      if (q0 + g + 8 < nq) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(own_row + q0 + g + 8) * W) = w1;
+      if (last_only) {
+        if (q0 + g == nq - 1) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(seq) * W) = w0;
+        if (q0 + g + 8 == nq - 1) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(seq) * W) = w1;
+      } else {
+        if (q0 + g < nq) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(own_row + q0 + g) * W) = w0;
+        if (q0 + g + 8 < nq) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(own_row + q0 + g + 8) * W) = w1;
+      }
     }
   }
+}
+
+// dst[r,:] = src[rows[r],:] (fp32): the residual rows of the pooled EOS positions, compacted for the final layer's MLP.
+__global__ void __launch_bounds__(256) gather_rows_f32_kernel(const float* __restrict__ src, const int* __restrict__ rows, int N,
+                                                             int W, float* __restrict__ dst) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= N) return;
+  const float4* in = reinterpret_cast<const float4*>(src + static_cast<size_t>(rows[r]) * W);
+  float4* o = reinterpret_cast<float4*>(dst + static_cast<size_t>(r) * W);
+  for (int c = lane; c < W / 4; c += 32) o[c] = in[c];
 }
 
 // F.normalize(x, dim=-1) in place (model.py:284): x / max(||x||, 1e-12). One warp per row.

@@ -377,6 +377,10 @@ class LeafEngine:
         check(self._lib.leaf_test_attention(self._h, _ptr(qkv), _ptr(meta), meta.shape[0], _ptr(out), _stream()))
         return out
 
+    def set_prune_last(self, on: bool):
+        """Final-layer pruning (out-proj / MLP on the pooled EOS rows only); on by default, bit-identical either way."""
+        check(self._lib.leaf_set_prune_last(self._h, 1 if on else 0))
+
     def launch_count(self, reset=False) -> int:
         return int(self._lib.leaf_launch_count(self._h, 1 if reset else 0))
 

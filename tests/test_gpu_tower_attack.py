@@ -119,6 +119,13 @@ def test_shared_prefix_is_bit_identical():
     ref = eng.encode_tokens(tok, ln, False, None)
     assert torch.equal(ded, ref)
     assert rows_ded < 0.8 * eng.encode_tokens(tok, ln, False, base).shape[0] * 77 and rows_ded < rows_shared
+    # final-layer pruning (out-proj / MLP on the pooled EOS rows only) changes no bit either
+    eng.set_prune_last(False)
+    try:
+        assert torch.equal(eng.encode_tokens(tok, ln, False, base, (B * n, n)), ded)
+        assert torch.equal(eng.encode_tokens(tok, ln, True, None), eng.encode_tokens(tok, ln, True, base, (B * n, n)))
+    finally:
+        eng.set_prune_last(True)
 
 
 def _golden_attack(golden_dir):
