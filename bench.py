@@ -300,14 +300,19 @@ def run_ours(a):
         del trainer, frozen2
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): one extra step with CUDA events around every GEMM launch ----
-    eng.set_timing(True)
     rec = []
-    device_step(*all_draws[-1], record=rec)
+    device_step(*all_draws[-1], record=rec)                  # row counts (synchronises) + warm-up after the legs above
     torch.cuda.synchronize()
-    gemm_ms, gemm_launches = eng.gemm_time_ms()
-    insitu = {name: round(eng.class_time_ms(i)[0], 3) for i, name in enumerate(("gemm", "layernorm", "attention", "pack_embed"))}
+    eng.set_timing(True)
+    for i in range(a.steps):                                 # averaged over the same number of steps as the headline
+        flush.fill_(i)
+        device_step(*all_draws[-1])                          # the draws whose row counts were recorded above
+    torch.cuda.synchronize()
+    per_step = lambda t: (t[0] / a.steps, t[1] // a.steps)
+    gemm_ms, gemm_launches = per_step(eng.gemm_time_ms())
+    insitu = {name: round(per_step(eng.class_time_ms(i))[0], 3) for i, name in enumerate(("gemm", "layernorm", "attention", "pack_embed"))}
     for epi, name in enumerate(("gemm_qkv_bf16", "gemm_fc1_bf16_act", "gemm_out_fc2_residual", "gemm_proj_f32", "gemm_fc2_residual")):
-        ms_epi, n_epi = eng.class_time_ms(4 + epi)
+        ms_epi, n_epi = per_step(eng.class_time_ms(4 + epi))
         if n_epi:
             insitu[name] = [round(ms_epi, 3), n_epi]
     eng.set_timing(False)

@@ -494,6 +494,17 @@ static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev,
   return LEAF_OK;
 }
 
+// causal attention over the packed rows (tower_kernels.cuh)
+static int launch_attention(leaf_engine* e, const __nv_bfloat16* qkv, const int4* meta, int N, __nv_bfloat16* out, int last_only,
+                            cudaStream_t st) {
+  const int H = e->cfg.heads, W = e->cfg.width;
+  const int grid = (N * H + ATT_WARPS - 1) / ATT_WARPS;
+  attention_kernel<<<grid, ATT_WARPS * 32, 0, st>>>(qkv, meta, N, H, W, out, last_only);
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
 extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* len, const int32_t* base, int32_t N,
                            int32_t dedup_rows, int32_t dedup_group, int32_t normalize, float* feat_out, void* stream) {
   if (!e || !tok || !len || !feat_out) return fail(LEAF_ERR_INVALID, "null argument");
@@ -531,10 +542,8 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
     const bool last = e->prune_last && l == e->cfg.layers - 1;
     {
       TimedSpan span(e, 2, st);
-      attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(e->big, e->meta, N, H, W, e->h, last ? 1 : 0);
+      if ((rc = launch_attention(e, e->big, e->meta, N, e->h, last ? 1 : 0, st))) return rc;
     }
-    e->launches++;
-    CK(cudaGetLastError());
     if (last) {
       {
         TimedSpan span(e, 3, st);
@@ -604,13 +613,8 @@ extern "C" int leaf_test_layernorm(leaf_handle_t e, const float* x, int32_t rows
 
 extern "C" int leaf_test_attention(leaf_handle_t e, const void* qkv, const int32_t* meta, int32_t N, void* out, void* stream) {
   if (!e || !qkv || !meta || !out || N <= 0) return fail(LEAF_ERR_INVALID, "bad argument");
-  const int H = e->cfg.heads;
-  attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const int4*>(meta), N, H, e->cfg.width,
-      static_cast<__nv_bfloat16*>(out));
-  e->launches++;
-  CK(cudaGetLastError());
-  return LEAF_OK;
+  return launch_attention(e, static_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const int4*>(meta), N,
+                          static_cast<__nv_bfloat16*>(out), 0, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int leaf_set_prune_last(leaf_handle_t e, int32_t on) {
@@ -777,7 +781,7 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
     float* x_next = (l + 1 < e->cfg.layers) ? t.L[l + 1].x_in : t.x_out;
     if ((rc = launch_layernorm(e, a.x_in, nullptr, M, nullptr, p.ln1_w, p.ln1_b, a.h1, st))) return rc;
     if ((rc = launch_gemm(e, a.h1, t.rows_cap, w.qkv_w, w.qkv_b, a.qkv, 3 * W, M, 3 * W, W, EPI_BF16, 0, nullptr, st))) return rc;
-    attention_kernel<<<(N * H + ATT_WARPS - 1) / ATT_WARPS, ATT_WARPS * 32, 0, st>>>(a.qkv, t.meta, N, H, W, a.o);
+    if ((rc = launch_attention(e, a.qkv, t.meta, N, a.o, 0, st))) return rc;
     e->launches++;
     CK(cudaMemcpyAsync(a.x_mid, a.x_in, xbytes, cudaMemcpyDeviceToDevice, st));
     if ((rc = launch_gemm(e, a.o, t.rows_cap, w.out_w, p.out_b, a.x_mid, W, M, W, W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;

@@ -209,11 +209,19 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
 // transformer.py:225,250-252,758-764; scale 1/sqrt(64)).
 //
 // One warp per (sequence, head); everything stays in registers: mma.sync.m16n8k16 (bf16, fp32 accumulate) for
-// Q.K^T and P.V, online softmax in fp32 (exp2 with the scale folded in). Operand fragments are read straight from
-// global memory with 16-byte loads: the contraction index of Q.K^T is permuted identically for Q and K so that a
-// lane's 8 contiguous bf16 feed two k-steps, and V fragments are transposed in registers with movmatrix, which
-// leaves every lane with 8 contiguous output columns (one 16-byte store per row and 32-column block).
-// tcgen05's 128-row tiles do not fit 2..77-row problems (1.2 % of the tower's FLOPs); this kernel is bandwidth bound.
+// Q.K^T and P.V, fp32 softmax (exp2 with the scale folded in). A sequence has at most 77 positions, so the whole score
+// row of a 16-query tile fits in registers (<= 5 key tiles): plain two-pass softmax, no running maximum, no rescaling.
+// Operand fragments are read straight from global memory with sm_100's 256-BIT loads (LDG.E.256): a lane reads 32
+// contiguous bytes, a quad one whole 128-byte head row, so a warp-wide load touches 8 full lines. With 128-bit loads
+// (8 half lines per instruction) the L1 tag stage was the busiest unit (ncu r19: L1/TEX 65 %, 56 % of the stall cycles
+// on its scoreboard); halving the requests per byte bought 15 % (tools/ab_attention.py, profiles/r34_attention_ab.log).
+// Lane (g, c) owns d = 16c .. 16c+15 of a head row; register i holds d = 16c + 2i, +1. The contraction index of Q.K^T is
+// permuted identically for Q and K (k-step j uses registers 2j, 2j+1), and the movmatrix-transposed V registers leave a
+// lane with 16 contiguous output columns (one 32-byte store per row).
+// The key tiles and then the value tiles form ONE stream of 2*NKT fragment sets that runs DEPTH sets ahead of the MMAs
+// through a register ring, so the first value tiles are in flight during the softmax (+6 % over loading at the point of
+// use; more registers per thread for occupancy, or fewer with spills, both measured slower).
+// tcgen05's 128-row tiles do not fit 2..77-row problems (1.2 % of the tower's FLOPs).
 //
 // meta[seq] = {own_row, t, p, base_row}: the sequence has t positions; positions [p, t) are its own packed rows
 // starting at own_row (they are the queries); keys/values of positions [0, p) are read from the rows of another
@@ -243,39 +251,53 @@ __device__ __forceinline__ float att_ex2(float x) {            // ex2.approx(-in
   return y;
 }
 
-// One 16-query tile against its NKT 16-key tiles. A sequence has at most 77 positions, so the whole score row fits in
-// registers (NKT <= 5): plain two-pass softmax, no running maximum and no rescaling of the output accumulator. The
-// kernel is instruction-issue bound, not bandwidth bound (ncu/in-situ: its time follows the SM clock); the online
-// form spent ~400 SASS instructions per key tile, most of them on the rescaling and the address arithmetic.
-template <int NKT>
+struct U8 { uint32_t r[8]; };
+__device__ __forceinline__ U8 ldg256(const void* p) {
+  U8 v;
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v.r[0]), "=r"(v.r[1]), "=r"(v.r[2]), "=r"(v.r[3]), "=r"(v.r[4]), "=r"(v.r[5]), "=r"(v.r[6]), "=r"(v.r[7])
+               : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg256(void* p, const U8& v) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.r[0]), "r"(v.r[1]), "r"(v.r[2]), "r"(v.r[3]),
+               "r"(v.r[4]), "r"(v.r[5]), "r"(v.r[6]), "r"(v.r[7])
+               : "memory");
+}
+
+template <int NKT, int DEPTH>
 __device__ __forceinline__ void attention_tile(const __nv_bfloat16* __restrict__ kbase, const __nv_bfloat16* __restrict__ vbase,
-                                               size_t ld, const uint32_t (&qf)[2][8], int pos0, int pos1, int t, int p,
-                                               int own_row, int base_row, int g, int c, float (&o)[8][4], float& inv0, float& inv1) {
+                                                  size_t ld, const U8& qa, const U8& qb, int pos0, int pos1, int t, int p,
+                                                  int own_row, int base_row, int g, int c, float (&o)[8][4], float& inv0, float& inv1) {
   const float sl2 = 0.125f * 1.4426950408889634f;          // 1/sqrt(64) * log2(e)
-  int roff[NKT][2];                                        // packed rows holding keys 16kt+8h+g
-#pragma unroll
-  for (int kt = 0; kt < NKT; ++kt)
+  constexpr int NS = 2 * NKT;                              // stream: K tiles 0..NKT-1, then V tiles 0..NKT-1
+  U8 ring[DEPTH][2];                                       // [slot][key half: keys 16kt+g, 16kt+8+g]
+  auto issue = [&](int si) {
+    const int kt = si < NKT ? si : si - NKT;
+    const __nv_bfloat16* src = si < NKT ? kbase : vbase;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int j = min(kt * 16 + h * 8 + g, t - 1);
-      roff[kt][h] = j < p ? base_row + j : own_row + (j - p);
+      ring[si % DEPTH][h] = ldg256(src + static_cast<size_t>(j < p ? base_row + j : own_row + (j - p)) * ld);
     }
+  };
+#pragma unroll
+  for (int si = 0; si < DEPTH && si < NS; ++si) issue(si);
   // ---- S = Q.K^T ----
   float s[NKT][2][4];
 #pragma unroll
-  for (int kt = 0; kt < NKT; ++kt)
+  for (int kt = 0; kt < NKT; ++kt) {
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
       s[kt][nt][0] = s[kt][nt][1] = s[kt][nt][2] = s[kt][nt][3] = 0.f;
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const uint4 kk = *reinterpret_cast<const uint4*>(kbase + roff[kt][nt] * ld + b * 32);
-        const uint32_t a_lo[4] = {qf[b][0], qf[b][4], qf[b][1], qf[b][5]};
-        const uint32_t a_hi[4] = {qf[b][2], qf[b][6], qf[b][3], qf[b][7]};
-        mma_bf16_16816(s[kt][nt], a_lo, kk.x, kk.y);
-        mma_bf16_16816(s[kt][nt], a_hi, kk.z, kk.w);
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t a[4] = {qa.r[2 * j], qb.r[2 * j], qa.r[2 * j + 1], qb.r[2 * j + 1]};
+        mma_bf16_16816(s[kt][nt], a, ring[kt % DEPTH][nt].r[2 * j], ring[kt % DEPTH][nt].r[2 * j + 1]);
       }
     }
+    if (kt + DEPTH < NS) issue(kt + DEPTH);
+  }
   // ---- causal mask and row maxima (rows g and g+8 live on the 4 lanes of a quad) ----
   float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -315,22 +337,21 @@ __device__ __forceinline__ void attention_tile(const __nv_bfloat16* __restrict__
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   inv0 = 1.f / l0;
   inv1 = 1.f / l1;
-  // ---- O = P.V : V fragments transposed in registers ----
+  // ---- O = P.V : V fragments transposed in registers; MMA i yields d = 16c + 2i, +1 ----
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
 #pragma unroll
-  for (int kt = 0; kt < NKT; ++kt)
+  for (int kt = 0; kt < NKT; ++kt) {
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const uint4 v0 = *reinterpret_cast<const uint4*>(vbase + roff[kt][0] * ld + b * 32);
-      const uint4 v1 = *reinterpret_cast<const uint4*>(vbase + roff[kt][1] * ld + b * 32);
-      const uint32_t v0r[4] = {v0.x, v0.y, v0.z, v0.w}, v1r[4] = {v1.x, v1.y, v1.z, v1.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        mma_bf16_16816(o[b * 4 + i], pf[kt], movmatrix_trans(v0r[i]), movmatrix_trans(v1r[i]));
-    }
+    for (int i = 0; i < 8; ++i)
+      mma_bf16_16816(o[i], pf[kt], movmatrix_trans(ring[(NKT + kt) % DEPTH][0].r[i]), movmatrix_trans(ring[(NKT + kt) % DEPTH][1].r[i]));
+    if (NKT + kt + DEPTH < NS) issue(NKT + kt + DEPTH);
+  }
 }
 
+// last_only (final layer): only the pooled EOS position feeds the output (transformer.py:661), so only the query tile
+// that holds it is computed and its row is written to out[seq] (one compact row per sequence).
+constexpr int ATT_DEPTH = 3;
 __global__ void __launch_bounds__(ATT_WARPS * 32, 4) attention_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                                        const int4* __restrict__ meta, int n_seq, int heads,
                                                                        int W, __nv_bfloat16* __restrict__ out,
@@ -344,53 +365,39 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 4) attention_kernel(const __nv
   const int nq = t - p;
   if (nq <= 0) return;                                       // duplicate of an earlier sequence: owns no rows
   const size_t ld = static_cast<size_t>(3) * W;
-  const __nv_bfloat16* qbase = qkv + head * 64 + c * 8;
+  const __nv_bfloat16* qbase = qkv + head * 64 + c * 16;
   const __nv_bfloat16* kbase = qbase + W;
   const __nv_bfloat16* vbase = qbase + 2 * W;
-  // last_only (final layer): only the pooled EOS position feeds the output (transformer.py:661), so only the query
-  // tile that holds it is computed and its row is written to out[seq] (one compact row per sequence).
   for (int q0 = last_only ? ((nq - 1) & ~15) : 0; q0 < nq; q0 += 16) {
-    // ---- Q fragments: rows q0+g and q0+g+8, two 32-wide d blocks, 8 contiguous bf16 per lane and block ----
     const int qi0 = min(q0 + g, nq - 1), qi1 = min(q0 + g + 8, nq - 1);
-    uint32_t qf[2][8];
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const uint4 r0 = *reinterpret_cast<const uint4*>(qbase + (static_cast<size_t>(own_row + qi0)) * ld + b * 32);
-      const uint4 r1 = *reinterpret_cast<const uint4*>(qbase + (static_cast<size_t>(own_row + qi1)) * ld + b * 32);
-      qf[b][0] = r0.x; qf[b][1] = r0.y; qf[b][2] = r0.z; qf[b][3] = r0.w;
-      qf[b][4] = r1.x; qf[b][5] = r1.y; qf[b][6] = r1.z; qf[b][7] = r1.w;
-    }
+    const U8 qa = ldg256(qbase + static_cast<size_t>(own_row + qi0) * ld);
+    const U8 qb = ldg256(qbase + static_cast<size_t>(own_row + qi1) * ld);
     const int pos0 = p + qi0, pos1 = p + qi1;               // absolute positions of the two query rows
     const int kmax = min(t - 1, p + q0 + 15);               // last key any query of the tile may see
     float o[8][4];
     float inv0, inv1;
+#define ATT_ARGS kbase, vbase, ld, qa, qb, pos0, pos1, t, p, own_row, base_row, g, c, o, inv0, inv1
     switch (kmax >> 4) {                                     // warp-uniform
-      case 0: attention_tile<1>(kbase, vbase, ld, qf, pos0, pos1, t, p, own_row, base_row, g, c, o, inv0, inv1); break;
-      case 1: attention_tile<2>(kbase, vbase, ld, qf, pos0, pos1, t, p, own_row, base_row, g, c, o, inv0, inv1); break;
-      case 2: attention_tile<3>(kbase, vbase, ld, qf, pos0, pos1, t, p, own_row, base_row, g, c, o, inv0, inv1); break;
-      case 3: attention_tile<4>(kbase, vbase, ld, qf, pos0, pos1, t, p, own_row, base_row, g, c, o, inv0, inv1); break;
-      default: attention_tile<5>(kbase, vbase, ld, qf, pos0, pos1, t, p, own_row, base_row, g, c, o, inv0, inv1); break;
+      case 0: attention_tile<1, ATT_DEPTH>(ATT_ARGS); break;
+      case 1: attention_tile<2, ATT_DEPTH>(ATT_ARGS); break;
+      case 2: attention_tile<3, ATT_DEPTH>(ATT_ARGS); break;
+      case 3: attention_tile<4, ATT_DEPTH>(ATT_ARGS); break;
+      default: attention_tile<5, ATT_DEPTH>(ATT_ARGS); break;
     }
-    // ---- normalise and store: lane holds columns 32b + 8c .. + 7 of rows g and g+8 ----
+#undef ATT_ARGS
+    U8 w0, w1;
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      uint4 w0, w1;
-      w0.x = pack_bf16x2(o[b * 4 + 0][0] * inv0, o[b * 4 + 0][1] * inv0);
-      w0.y = pack_bf16x2(o[b * 4 + 1][0] * inv0, o[b * 4 + 1][1] * inv0);
-      w0.z = pack_bf16x2(o[b * 4 + 2][0] * inv0, o[b * 4 + 2][1] * inv0);
-      w0.w = pack_bf16x2(o[b * 4 + 3][0] * inv0, o[b * 4 + 3][1] * inv0);
-      w1.x = pack_bf16x2(o[b * 4 + 0][2] * inv1, o[b * 4 + 0][3] * inv1);
-      w1.y = pack_bf16x2(o[b * 4 + 1][2] * inv1, o[b * 4 + 1][3] * inv1);
-      w1.z = pack_bf16x2(o[b * 4 + 2][2] * inv1, o[b * 4 + 2][3] * inv1);
-      w1.w = pack_bf16x2(o[b * 4 + 3][2] * inv1, o[b * 4 + 3][3] * inv1);
-      __nv_bfloat16* ob = out + head * 64 + b * 32 + c * 8;
-      if (last_only) {
-        if (q0 + g == nq - 1) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(seq) * W) = w0;
-        if (q0 + g + 8 == nq - 1) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(seq) * W) = w1;
-      } else {
-        if (q0 + g < nq) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(own_row + q0 + g) * W) = w0;
-        if (q0 + g + 8 < nq) *reinterpret_cast<uint4*>(ob + static_cast<size_t>(own_row + q0 + g + 8) * W) = w1;
-      }
+    for (int i = 0; i < 8; ++i) {
+      w0.r[i] = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+      w1.r[i] = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+    }
+    __nv_bfloat16* ob = out + head * 64 + c * 16;
+    if (last_only) {
+      if (q0 + g == nq - 1) stg256(ob + static_cast<size_t>(seq) * W, w0);
+      if (q0 + g + 8 == nq - 1) stg256(ob + static_cast<size_t>(seq) * W, w1);
+    } else {
+      if (q0 + g < nq) stg256(ob + static_cast<size_t>(own_row + q0 + g) * W, w0);
+      if (q0 + g + 8 < nq) stg256(ob + static_cast<size_t>(own_row + q0 + g + 8) * W, w1);
     }
   }
 }

@@ -371,9 +371,10 @@ class LeafEngine:
         check(self._lib.leaf_test_layernorm(self._h, _ptr(x), x.shape[0], _ptr(gamma), _ptr(beta), _ptr(y), _stream()))
         return y
 
-    def test_attention(self, qkv, meta):
+    def test_attention(self, qkv, meta, out=None):
         """meta int32 [N,4] = {own_row, t, p, base_row} per sequence."""
-        out = torch.zeros((qkv.shape[0], self.width), dtype=torch.bfloat16, device=qkv.device)
+        if out is None:
+            out = torch.zeros((qkv.shape[0], self.width), dtype=torch.bfloat16, device=qkv.device)
         check(self._lib.leaf_test_attention(self._h, _ptr(qkv), _ptr(meta), meta.shape[0], _ptr(out), _stream()))
         return out
 
