@@ -311,7 +311,7 @@ def run_ours(a):
     per_step = lambda t: (t[0] / a.steps, t[1] // a.steps)
     gemm_ms, gemm_launches = per_step(eng.gemm_time_ms())
     insitu = {name: round(per_step(eng.class_time_ms(i))[0], 3) for i, name in enumerate(("gemm", "layernorm", "attention", "pack_embed"))}
-    for epi, name in enumerate(("gemm_qkv_bf16", "gemm_fc1_bf16_act", "gemm_out_fc2_residual", "gemm_proj_f32", "gemm_fc2_residual")):
+    for epi, name in enumerate(("gemm_qkv_bf16", "gemm_fc1_bf16_act", "gemm_out_fc2_residual", "gemm_proj_f32", "gemm_fc2_residual", "gemm_out_bf16")):
         ms_epi, n_epi = per_step(eng.class_time_ms(4 + epi))
         if n_epi:
             insitu[name] = [round(ms_epi, 3), n_epi]

@@ -103,6 +103,7 @@ struct leaf_engine {
   float* x = nullptr;                 // [rows_cap, W] fp32 residual stream
   __nv_bfloat16* h = nullptr;         // [rows_cap, W]  LN output / attention output
   __nv_bfloat16* big = nullptr;       // [rows_cap, 4W] qkv (3W) or MLP hidden (4W)
+  __nv_bfloat16* dlt = nullptr;       // [rows_cap, W]  out-proj result of the current layer (added to x by fc2's epilogue)
   __nv_bfloat16* pooled = nullptr;    // [max_seqs, W]
   float* xc = nullptr;                // [max_seqs, W] fp32 residual rows of the pooled positions (final layer, compact)
   int* first_of = nullptr;            // [max_seqs] sequence whose rows stand for sequence i
@@ -114,8 +115,8 @@ struct leaf_engine {
   bool timing = false;
   struct Span { cudaEvent_t a, b; int cat; };
   std::vector<Span> spans;            // cat: 0 GEMM, 1 LayerNorm, 2 attention, 3 everything else of the encode
-  double span_ms[9] = {0};         // 4 + epi: the GEMM launches of one epilogue kind (also counted in class 0);
-  int span_n[9] = {0};             // 8: the residual GEMMs with K > N (fc2), counted in class 6 as well
+  double span_ms[10] = {0};        // 4 + epi: the GEMM launches of one epilogue kind (also counted in class 0);
+  int span_n[10] = {0};            // 8: the residual GEMMs with K > N (fc2), counted in class 6 as well; 9: bf16 store, N == K (out-proj)
   std::vector<cudaEvent_t> event_pool;
   std::map<std::tuple<const void*, long, long, int>, CUtensorMap> tmaps;
 };
@@ -164,7 +165,8 @@ struct TimedSpan {
 
 // C[M,N] = A[M,K] . Bt[N,K]^T with the fused epilogue `epi`
 static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, const __nv_bfloat16* Bt, const float* bias,
-                       void* C, int ldc, int M, int N, int K, int epi, int act, const int* m_dev, cudaStream_t st) {
+                       void* C, int ldc, int M, int N, int K, int epi, int act, const int* m_dev, cudaStream_t st,
+                       const __nv_bfloat16* delta = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(LEAF_ERR_INVALID, "GEMM shape %dx%dx%d", M, N, K);
   if (N % 8 != 0) return fail(LEAF_ERR_INVALID, "GEMM N (%d) must be a multiple of 8", N);
   CUtensorMap ta, tb;
@@ -176,10 +178,10 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   if (rc) return rc;
   GemmParams p;
   p.tx_bytes = static_cast<uint32_t>(a_box + b_box) * GEMM_BK * 2 * 2;       // both CTAs of the pair
-  p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act;
+  p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act; p.delta = delta;
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
   const long tiles = static_cast<long>(m_tiles) * n_tiles;
-  TimedSpan span(e, (epi == EPI_F32_RESIDUAL && K > N) ? 8 : 4 + epi, st);
+  TimedSpan span(e, (epi == EPI_F32_RESIDUAL && K > N) ? 8 : (epi == EPI_BF16 && K == N) ? 9 : 4 + epi, st);
   const int pairs_max = e->sm_count / 2;
   const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
   cudaLaunchConfig_t cfg{};
@@ -240,8 +242,8 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
 }
 
 static void free_workspace(leaf_engine* e) {
-  cudaFree(e->x); cudaFree(e->h); cudaFree(e->big); cudaFree(e->pooled); cudaFree(e->xc); cudaFree(e->first_of);
-  e->xc = nullptr; e->first_of = nullptr;
+  cudaFree(e->x); cudaFree(e->h); cudaFree(e->big); cudaFree(e->pooled); cudaFree(e->xc); cudaFree(e->first_of); cudaFree(e->dlt);
+  e->xc = nullptr; e->first_of = nullptr; e->dlt = nullptr;
   cudaFree(e->cu); cudaFree(e->eos_row); cudaFree(e->total_rows); cudaFree(e->pfx); cudaFree(e->own_len); cudaFree(e->dup_of); cudaFree(e->meta);
   e->x = nullptr; e->h = nullptr; e->big = nullptr; e->pooled = nullptr;
   e->cu = e->eos_row = e->total_rows = e->pfx = e->own_len = e->dup_of = nullptr;
@@ -440,6 +442,7 @@ extern "C" int leaf_reserve(leaf_handle_t e, int32_t max_seqs) {
   CK(cudaMalloc(&e->x, rows * W * 4));
   CK(cudaMalloc(&e->h, rows * W * 2));
   CK(cudaMalloc(&e->big, rows * 4 * W * 2));
+  CK(cudaMalloc(&e->dlt, rows * W * 2));
   CK(cudaMalloc(&e->pooled, (static_cast<size_t>(max_seqs) + 128) * W * 2));
   CK(cudaMalloc(&e->xc, (static_cast<size_t>(max_seqs) + 128) * W * 4));
   CK(cudaMalloc(&e->first_of, static_cast<size_t>(max_seqs) * 4));
@@ -473,7 +476,8 @@ extern "C" int leaf_expand_tokenize(leaf_handle_t e, const uint8_t* caps, const 
 }
 
 static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev, int rows_max, const int* gather,
-                            const float* g, const float* b, __nv_bfloat16* y, cudaStream_t st) {
+                            const float* g, const float* b, __nv_bfloat16* y, cudaStream_t st,
+                            const __nv_bfloat16* delta = nullptr) {
   const int W = e->cfg.width;
   const int vpl = W / 128;
   TimedSpan span(e, 1, st);
@@ -482,7 +486,7 @@ static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev,
   const int cap = e->sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-#define LN_CASE(V) case V: layernorm_bf16_kernel<V><<<blocks, 256, 0, st>>>(x, rows_dev, rows_max, gather, W, g, b, e->cfg.ln_eps, y); break;
+#define LN_CASE(V) case V: layernorm_bf16_kernel<V><<<blocks, 256, 0, st>>>(x, rows_dev, rows_max, gather, W, g, b, e->cfg.ln_eps, y, delta); break;
   switch (vpl) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
     LN_CASE(9) LN_CASE(10) LN_CASE(11) LN_CASE(12) LN_CASE(13) LN_CASE(14) LN_CASE(15) LN_CASE(16)
@@ -540,26 +544,33 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
     // the key/value projection runs on ONE row per sequence: attention writes the EOS query's output to h[seq], the
     // residual rows are compacted into xc, and out-proj / LayerNorm / MLP see N rows instead of the packed row count.
     const bool last = e->prune_last && l == e->cfg.layers - 1;
+    const __nv_bfloat16* dl = e->dlt;
     {
       TimedSpan span(e, 2, st);
       if ((rc = launch_attention(e, e->big, e->meta, N, e->h, last ? 1 : 0, st))) return rc;
     }
+    // The attention branch's out-proj result stays OUT of the fp32 residual stream for now: it is stored as a bf16
+    // delta (2 B per element, no read), LayerNorm normalises x + delta on the fly, and fc2's epilogue writes
+    // x + delta + mlp back in one read-modify-write. A separate x += out-proj pass made the K = W out-proj GEMM the one
+    // launch whose epilogue (8 B of fp32 residual traffic per 2 KFLOP) outran L2/HBM: 379 us against 230 us with a bf16
+    // store at 130 k rows (tools/ab_gemm.py, profiles/r38_gemm_ab.log). 16-bit Linear outputs are what the reference's
+    // own autocast path produces; the fp32 stream itself is untouched.
     if (last) {
       {
         TimedSpan span(e, 3, st);
         gather_rows_f32_kernel<<<(N + 7) / 8, 256, 0, st>>>(e->x, e->eos_row, N, W, e->xc);
         e->launches++;
       }
-      if ((rc = launch_gemm(e, e->h, e->rows_cap, w.out_w, p.out_b, e->xc, W, N, W, W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-      if ((rc = launch_layernorm(e, e->xc, nullptr, N, nullptr, p.ln2_w, p.ln2_b, e->h, st))) return rc;
+      if ((rc = launch_gemm(e, e->h, e->rows_cap, w.out_w, p.out_b, e->dlt, W, N, W, W, EPI_BF16, 0, nullptr, st))) return rc;
+      if ((rc = launch_layernorm(e, e->xc, nullptr, N, nullptr, p.ln2_w, p.ln2_b, e->h, st, dl))) return rc;
       if ((rc = launch_gemm(e, e->h, e->rows_cap, w.fc1_w, p.fc1_b, e->big, 4 * W, N, 4 * W, W, EPI_BF16_ACT, e->cfg.activation, nullptr, st))) return rc;
-      if ((rc = launch_gemm(e, e->big, e->rows_cap, w.fc2_w, p.fc2_b, e->xc, W, N, W, 4 * W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+      if ((rc = launch_gemm(e, e->big, e->rows_cap, w.fc2_w, p.fc2_b, e->xc, W, N, W, 4 * W, EPI_F32_RESIDUAL, 0, nullptr, st, dl))) return rc;
       break;
     }
-    if ((rc = launch_gemm(e, e->h, e->rows_cap, w.out_w, p.out_b, e->x, W, rows_max, W, W, EPI_F32_RESIDUAL, 0, e->total_rows, st))) return rc;
-    if ((rc = launch_layernorm(e, e->x, e->total_rows, rows_max, nullptr, p.ln2_w, p.ln2_b, e->h, st))) return rc;
+    if ((rc = launch_gemm(e, e->h, e->rows_cap, w.out_w, p.out_b, e->dlt, W, rows_max, W, W, EPI_BF16, 0, e->total_rows, st))) return rc;
+    if ((rc = launch_layernorm(e, e->x, e->total_rows, rows_max, nullptr, p.ln2_w, p.ln2_b, e->h, st, dl))) return rc;
     if ((rc = launch_gemm(e, e->h, e->rows_cap, w.fc1_w, p.fc1_b, e->big, 4 * W, rows_max, 4 * W, W, EPI_BF16_ACT, e->cfg.activation, e->total_rows, st))) return rc;
-    if ((rc = launch_gemm(e, e->big, e->rows_cap, w.fc2_w, p.fc2_b, e->x, W, rows_max, W, 4 * W, EPI_F32_RESIDUAL, 0, e->total_rows, st))) return rc;
+    if ((rc = launch_gemm(e, e->big, e->rows_cap, w.fc2_w, p.fc2_b, e->x, W, rows_max, W, 4 * W, EPI_F32_RESIDUAL, 0, e->total_rows, st, dl))) return rc;
   }
   if (e->prune_last) rc = launch_layernorm(e, e->xc, nullptr, N, e->first_of, e->wp.lnf_w, e->wp.lnf_b, e->pooled, st);
   else rc = launch_layernorm(e, e->x, nullptr, N, e->eos_row, e->wp.lnf_w, e->wp.lnf_b, e->pooled, st);
@@ -644,13 +655,13 @@ extern "C" int leaf_set_timing(leaf_handle_t e, int32_t on) {
   if (e->timing) {                               // a new measurement starts from zero
     int32_t dummy;
     leaf_timing_ms(e, 0, &dummy);
-    for (int i = 0; i < 9; ++i) { e->span_ms[i] = 0; e->span_n[i] = 0; }
+    for (int i = 0; i < 10; ++i) { e->span_ms[i] = 0; e->span_n[i] = 0; }
   }
   return LEAF_OK;
 }
 
 extern "C" double leaf_timing_ms(leaf_handle_t e, int32_t which, int32_t* launches) {
-  if (!e || which < 0 || which > 8) return 0.0;
+  if (!e || which < 0 || which > 9) return 0.0;
   if (!e->spans.empty()) {                       // fold the recorded spans into the per-category totals
     for (auto& sp : e->spans) {
       cudaEventSynchronize(sp.b);
@@ -782,7 +793,6 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
     if ((rc = launch_layernorm(e, a.x_in, nullptr, M, nullptr, p.ln1_w, p.ln1_b, a.h1, st))) return rc;
     if ((rc = launch_gemm(e, a.h1, t.rows_cap, w.qkv_w, w.qkv_b, a.qkv, 3 * W, M, 3 * W, W, EPI_BF16, 0, nullptr, st))) return rc;
     if ((rc = launch_attention(e, a.qkv, t.meta, N, a.o, 0, st))) return rc;
-    e->launches++;
     CK(cudaMemcpyAsync(a.x_mid, a.x_in, xbytes, cudaMemcpyDeviceToDevice, st));
     if ((rc = launch_gemm(e, a.o, t.rows_cap, w.out_w, p.out_b, a.x_mid, W, M, W, W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
     if ((rc = launch_layernorm(e, a.x_mid, nullptr, M, nullptr, p.ln2_w, p.ln2_b, a.h2, st))) return rc;

@@ -190,21 +190,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint8_t* stage_buf = smem_gen + GEMM2_STAGES * GEMM2_STAGE_BYTES + warp * EPI_STAGE_BYTES;
     int acc = 0;
     uint32_t acc_phase = 0;
-    auto prefetch_residual = [&](int tile) {
-      if (EPI != EPI_F32_RESIDUAL || tile >= total_tiles) return;
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      const int row = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32 + lane;
-      if (row >= M) return;
-      const int col0 = n_blk * GEMM_BN + part * 64;
-      const float* r = reinterpret_cast<const float*>(p.C) + static_cast<size_t>(row) * p.ldc + col0;
-#pragma unroll
-      for (int c = 0; c < 64; c += 32)
-        if (col0 + c < p.N) prefetch_l2(r + c);
-    };
-    prefetch_residual(pair);
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
       const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
-      prefetch_residual(tile + n_pairs);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row0 = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32;

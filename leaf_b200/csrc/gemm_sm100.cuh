@@ -38,6 +38,7 @@ struct GemmParams {
   int N, K;
   const float* bias;      // [N] or nullptr
   void* C;                // bf16 or fp32 [M, ldc]
+  const __nv_bfloat16* delta;   // EPI_F32_RESIDUAL only, may be null: bf16 [M, ldc] added to the residual as well
   int ldc;
   int act;
   uint32_t tx_bytes;      // bytes one pipeline stage receives (TMA boxes are clamped to small tensors)
@@ -162,10 +163,6 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ float quick_gelu(float x) {                   // x sigmoid(1.702 x), transformer.py:33-36
   return x * fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));
 }
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
 // Fused epilogue of one 32-row x 32-column chunk of the accumulator. Each lane arrives with one ROW of the chunk
 // (v = raw fp32 bits from TMEM, tcgen05.ld 32x32b); storing that directly would touch 32 different 128-byte lines per
 // instruction (ncu r3: LSU wavefronts, not the tensor pipe, paced the K=1024 GEMMs). The chunk is bounced through a
@@ -247,6 +244,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
   } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+      // the bf16 delta is fetched per pass (8 registers) rather than with the residual: the kernel sits at its register
+      // cap, and the only user (fc2, K = 4W) has four times the mainloop time of the other GEMMs to hide the latency in
+      uint2 dl[4];
+      if (EPI == EPI_F32_RESIDUAL && p.delta) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = row0 + it * 8 + (lane >> 2), col = col0 + h * 16 + c * 4;
+          dl[it] = (row < M && col < p.N) ? *reinterpret_cast<const uint2*>(p.delta + static_cast<size_t>(row) * p.ldc + col)
+                                          : make_uint2(0u, 0u);
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         *reinterpret_cast<float4*>(stage + lane * 80 + q * 16) =
@@ -259,7 +267,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
         float4 o = *reinterpret_cast<const float4*>(stage + r * 80 + c * 16);
         if (col < p.N && row0 + r < M) {
           if (EPI == EPI_F32_RESIDUAL) {
-            const float4 x = res.x[h * 4 + it];
+            float4 x = res.x[h * 4 + it];
+            if (p.delta) {                              // x + delta first: the sum LayerNorm saw (leaf_encode)
+              const uint2 d = dl[it];
+              const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.x));
+              const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.y));
+              x.x += d0.x; x.y += d0.y; x.z += d1.x; x.w += d1.y;
+            }
             o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
           }
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + static_cast<size_t>(row0 + r) * p.ldc + col) = o;

@@ -162,12 +162,15 @@ __global__ void __launch_bounds__(256) embed_kernel(const int* __restrict__ tok,
 // LayerNorm over fp32 rows -> bf16 (F.layer_norm, transformer.py:24-30), two-pass in registers.
 // W = 128 * V4 floats... one warp per row, lane owns W/32 contiguous-by-4 elements. Rows from a device count.
 // gather != nullptr: output row r reads input row gather[r] (EOS pooling, transformer.py:661).
+// delta != nullptr: the row normalised is x[row] + delta[row] (bf16): the attention branch's out-proj result, which
+// leaf_encode keeps apart from the fp32 residual stream until fc2's epilogue folds both in (see leaf_encode).
 // ---------------------------------------------------------------------------------------------
 template <int VPL /* float4 per lane */>
 __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __restrict__ x, const int* __restrict__ rows_dev,
                                                             int rows_max, const int* __restrict__ gather, int W,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                            float eps, __nv_bfloat16* __restrict__ y) {
+                                                            float eps, __nv_bfloat16* __restrict__ y,
+                                                            const __nv_bfloat16* __restrict__ delta = nullptr) {
   const int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -177,10 +180,19 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
     float4 v[VPL];
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      v[i] = in[lane + 32 * i];
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < VPL; ++i) v[i] = in[lane + 32 * i];
+    if (delta) {
+      const uint2* dp = reinterpret_cast<const uint2*>(delta + static_cast<size_t>(src) * W);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const uint2 d = dp[lane + 32 * i];
+        const float2 d0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.x));
+        const float2 d1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&d.y));
+        v[i].x += d0.x; v[i].y += d0.y; v[i].z += d1.x; v[i].w += d1.y;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(s) / static_cast<float>(W);
     float q = 0.f;
 #pragma unroll
