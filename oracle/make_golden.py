@@ -140,6 +140,28 @@ def gen_tower():
     print("tower fixtures", {k: v.shape for k, v in out.items()})
 
 
+def gen_convert_ids():
+    """The one known-answer input the reference's own tower checks use (conversion/convert_2.py:252-253 and
+    convert_to_openclip.py:155-156 compare open_clip with HF on ids [49406, 1, ..., 76] at atol 1e-4): the row has no
+    end-of-text token, so argmax(ids) pools position 0, the start-of-text token. Plus rows whose maximum sits first /
+    last / in the middle of a full 77-token row."""
+    ids = np.zeros((4, 77), dtype=np.int64)
+    ids[0] = [49406] + list(range(1, 77))
+    ids[1] = list(range(1, 77)) + [49407]
+    ids[2] = [49406] + list(range(100, 137)) + [49407] + list(range(200, 238))
+    ids[3] = [49406, 320, 49407] + [0] * 74
+    tokens = torch.from_numpy(ids)
+    out = {"tokens": ids}
+    for name in ("tiny", "small"):
+        cfg = synth.TOWERS[name]
+        sd = synth.random_tower_state_dict(cfg, seed=23, exact_numpy=True)
+        model = build_ref_clip(cfg, sd)
+        with torch.no_grad():
+            out[name] = model.encode_text(tokens, normalize=False).numpy()
+    np.savez_compressed(os.path.join(OUT, "convert_ids_golden.npz"), **out)
+    print("convert-ids fixtures", {k: v.shape for k, v in out.items()})
+
+
 def gen_attack():
     tok = open_clip.get_tokenizer("ViT-L-14")
     cfg = synth.TOWERS["tiny"]
@@ -267,6 +289,10 @@ def gen_hf_tokenizer():
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
+    if sys.argv[1:] == ["convert_ids"]:                       # add this fixture without regenerating the others
+        gen_convert_ids()
+        sys.exit(0)
+    gen_convert_ids()
     gen_edit()
     gen_tokenizer()
     gen_tower()

@@ -38,6 +38,24 @@ def test_tower_golden_fixtures(golden_dir):
         assert torch.allclose(fn.norm(dim=-1), torch.ones(fn.shape[0]), atol=1e-5)
 
 
+def test_tower_on_the_reference_conversion_check_ids(golden_dir):
+    """The reference's own tower check input, ids [49406, 1..76] (conversion/convert_2.py:252-253): the row has no
+    end-of-text token, so the pooled position is 0 and the engine computes ONE row for it; plus full 77-token rows whose
+    maximum sits last / mid-row (positions after it are dead) and a 3-token row."""
+    from leaf_b200 import synth
+    from leaf_b200.tower import LeafTextTower
+    z = np.load(os.path.join(golden_dir, "convert_ids_golden.npz"))
+    tokens = torch.from_numpy(z["tokens"]).cuda()
+    for name in ("tiny", "small"):
+        cfg = synth.TOWERS[name]
+        tower = LeafTextTower(synth.random_tower_state_dict(cfg, seed=23, exact_numpy=True), heads=cfg.heads)
+        f = tower.encode_text(tokens).cpu()
+        assert tower.leaf_engine.last_rows() == 1 + 77 + 39 + 3
+        want = torch.from_numpy(z[name])
+        assert _cos(f, want).min() >= COS_MIN, (name, _cos(f, want))
+        assert (f - want).norm() / want.norm() < 1e-2
+
+
 def test_tower_hf_layout_binds_identically():
     """The HF CLIPTextModel weight layout (split q/k/v, text_projection.weight = P^T; conversion/convert_2.py:37-99)
     must give the same features as the open_clip layout."""
