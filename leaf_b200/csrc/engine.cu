@@ -917,7 +917,7 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
       if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(g.out_w), W, W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
     }
     if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.out_b), st))) return rc;
-    attention_bwd_kernel<<<dim3(N, H), ATTB_THREADS, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16);   // dqkv [M,3W] bf16
+    attention_bwd_kernel<<<dim3(N, H), 32, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16);   // dqkv [M,3W] bf16
     e->launches++;
     CK(cudaGetLastError());
     if ((rc = launch_gemm(e, t.d16, cap, w.qkv_wT, nullptr, t.dtmp, W, M, W, 3 * W, EPI_F32, 0, nullptr, st))) return rc;        // dh1 [M,W]

@@ -171,80 +171,236 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
-// ---- causal attention backward, one CTA per (sequence, head), fp32 in shared memory -------------------------------------
+// ---- causal attention backward on the tensor cores: one warp per (sequence, head) ------------------------------------------
 // qkv bf16 [rows,3W], o bf16 [rows,W] (forward output), dout fp32 [rows,W] -> dqkv bf16 [rows,3W].
 //   P = softmax(scale Q K^T + causal), D_i = sum_d dO_id O_id, dP = dO V^T, dS = P o (dP - D),
 //   dV = P^T dO, dQ = scale dS K, dK = scale dS^T Q.
-constexpr int ATTB_THREADS = 256;
-__host__ __device__ constexpr int attb_smem_bytes(int T) { return (4 * T * 65 + 2 * T * (T + 1) + T) * 4; }
+// Q, K, V and dO (rounded to bf16, like every other GEMM operand of the backward) are staged in shared memory with rows
+// padded to 72 elements (ldmatrix conflict-free), zero beyond the sequence. Pass 1 walks the 16-query tiles: S and dP of
+// the whole (<= 5 key tiles) row block sit in registers (mma.sync.m16n8k16, fp32 accumulate), softmax and dS in fp32, dQ
+// straight from the dS accumulator registers (a C fragment pair IS the next product's A fragment); P and dS go to
+// shared memory as bf16. Pass 2 walks the key tiles and reads them back TRANSPOSED (ldmatrix.trans) for dV and dK.
+// The scalar fp32 version this replaces (one CTA per pair, 221 us per layer at B = 128) was the largest K4 kernel.
+// T16 = longest sequence of the batch rounded up to 16 (sizes the shared-memory arrays).
+constexpr int ATTB_PITCH = 72;
+__host__ __device__ constexpr int attb_smem_bytes(int T) {
+  const int T16 = (T + 15) / 16 * 16;
+  return 4 * T16 * ATTB_PITCH * 2 + 2 * T16 * (T16 + 8) * 2 + T16 * 4;
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 
-// T = longest sequence of the batch (sizes the shared-memory arrays, so short captions fit several CTAs per SM)
-__global__ void __launch_bounds__(ATTB_THREADS) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv,
-                                                                     const __nv_bfloat16* __restrict__ o,
-                                                                     const float* __restrict__ dout, const int4* __restrict__ meta,
-                                                                     int W, int T, __nv_bfloat16* __restrict__ dqkv) {
-  extern __shared__ float sm[];
-  float* Q = sm;
-  float* K = Q + T * 65;
-  float* V = K + T * 65;
-  float* dO = V + T * 65;
-  float* P = dO + T * 65;
-  float* dS = P + T * (T + 1);
-  float* Dv = dS + T * (T + 1);
-  const int TP = T + 1;
-  const int seq = blockIdx.x, head = blockIdx.y;
+// Pass 1 for the query tile qi (NKT = qi + 1 key tiles under the causal mask, no shared prefix in training batches)
+template <int NKT>
+__device__ __forceinline__ void attb_query_tile(uint32_t sQ, uint32_t sK, uint32_t sV, uint32_t sdO, __nv_bfloat16* Ps, __nv_bfloat16* dSs,
+                                                const float* Dv, int PP, int lane, float (&dq)[8][4]) {
+  constexpr int qi = NKT - 1;
+  const int g = lane >> 2, c = lane & 3;
+  const float sl2 = 0.125f * 1.4426950408889634f;
+  // A fragments of Q and dO rows 16qi.., four k-steps of 16 over d
+  const uint32_t a_off = static_cast<uint32_t>(((16 * qi + (lane & 7) + 8 * ((lane >> 3) & 1)) * ATTB_PITCH + 8 * (lane >> 4)) * 2);
+  uint32_t aq[4][4], ado[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    ldsm_x4(aq[ks], sQ + a_off + ks * 32);
+    ldsm_x4(ado[ks], sdO + a_off + ks * 32);
+  }
+  float s[NKT][2][4], dp[NKT][2][4];
+  // B fragments of K / V stored [key][d]: matrices (keys 0-7, d 0-7), (keys 0-7, d 8-15), (keys 8-15, d 0-7), (keys 8-15, d 8-15)
+  const uint32_t b_off = static_cast<uint32_t>((((lane & 7) + 8 * (lane >> 4)) * ATTB_PITCH + 8 * ((lane >> 3) & 1)) * 2);
+#pragma unroll
+  for (int kj = 0; kj < NKT; ++kj) {
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[kj][nt][e] = dp[kj][nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      uint32_t bk[4], bv[4];
+      ldsm_x4(bk, sK + b_off + (16 * kj * ATTB_PITCH + 16 * ks) * 2);
+      ldsm_x4(bv, sV + b_off + (16 * kj * ATTB_PITCH + 16 * ks) * 2);
+      mma_bf16_16816(s[kj][0], aq[ks], bk[0], bk[1]);
+      mma_bf16_16816(s[kj][1], aq[ks], bk[2], bk[3]);
+      mma_bf16_16816(dp[kj][0], ado[ks], bv[0], bv[1]);
+      mma_bf16_16816(dp[kj][1], ado[ks], bv[2], bv[3]);
+    }
+  }
+  // causal mask, softmax rows g and g+8 of the tile
+  const int i0 = 16 * qi + g, i1 = i0 + 8;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+  for (int kj = 0; kj < NKT; ++kj)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 16 * kj + 8 * nt + 2 * c + e;
+        if (j > i0) s[kj][nt][e] = -INFINITY;
+        if (j > i1) s[kj][nt][2 + e] = -INFINITY;
+        mx0 = fmaxf(mx0, s[kj][nt][e]);
+        mx1 = fmaxf(mx1, s[kj][nt][2 + e]);
+      }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+  for (int kj = 0; kj < NKT; ++kj)
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[kj][nt][e] = att_ex2((s[kj][nt][e] - mx0) * sl2);
+        s[kj][nt][2 + e] = att_ex2((s[kj][nt][2 + e] - mx1) * sl2);
+        l0 += s[kj][nt][e];
+        l1 += s[kj][nt][2 + e];
+      }
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = 1.f / l0, inv1 = 1.f / l1, d0 = Dv[i0], d1 = Dv[i1];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+  // K stored [key][d] read as the B operand [k = key][n = d]: transposed 8x8 loads
+  const uint32_t bt_off = static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * ATTB_PITCH + 8 * (lane >> 4)) * 2);
+#pragma unroll
+  for (int kj = 0; kj < NKT; ++kj) {
+    uint32_t ads[4];                                       // dS tile as the A fragment of dQ += dS K
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      const float p00 = s[kj][nt][0] * inv0, p01 = s[kj][nt][1] * inv0, p10 = s[kj][nt][2] * inv1, p11 = s[kj][nt][3] * inv1;
+      const float t00 = 0.125f * p00 * (dp[kj][nt][0] - d0), t01 = 0.125f * p01 * (dp[kj][nt][1] - d0);
+      const float t10 = 0.125f * p10 * (dp[kj][nt][2] - d1), t11 = 0.125f * p11 * (dp[kj][nt][3] - d1);
+      const uint32_t pp0 = pack_bf16x2(p00, p01), pp1 = pack_bf16x2(p10, p11);
+      ads[2 * nt] = pack_bf16x2(t00, t01);
+      ads[2 * nt + 1] = pack_bf16x2(t10, t11);
+      const int col = 16 * kj + 8 * nt + 2 * c;
+      *reinterpret_cast<uint32_t*>(Ps + i0 * PP + col) = pp0;
+      *reinterpret_cast<uint32_t*>(Ps + i1 * PP + col) = pp1;
+      *reinterpret_cast<uint32_t*>(dSs + i0 * PP + col) = ads[2 * nt];
+      *reinterpret_cast<uint32_t*>(dSs + i1 * PP + col) = ads[2 * nt + 1];
+    }
+#pragma unroll
+    for (int nd = 0; nd < 4; ++nd) {                       // d blocks of 16: two n8 tiles each
+      uint32_t bk[4];
+      ldsm_x4_t(bk, sK + bt_off + (16 * kj * ATTB_PITCH + 16 * nd) * 2);
+      mma_bf16_16816(dq[2 * nd], ads, bk[0], bk[1]);
+      mma_bf16_16816(dq[2 * nd + 1], ads, bk[2], bk[3]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
+                                                           const float* __restrict__ dout, const int4* __restrict__ meta,
+                                                           int W, int T, __nv_bfloat16* __restrict__ dqkv) {
+  extern __shared__ __align__(16) uint8_t attb_sm[];
+  const int T16 = (T + 15) / 16 * 16, PP = T16 + 8;
+  __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attb_sm);
+  __nv_bfloat16* Ks = Qs + T16 * ATTB_PITCH;
+  __nv_bfloat16* Vs = Ks + T16 * ATTB_PITCH;
+  __nv_bfloat16* dOs = Vs + T16 * ATTB_PITCH;
+  __nv_bfloat16* Ps = dOs + T16 * ATTB_PITCH;
+  __nv_bfloat16* dSs = Ps + T16 * PP;
+  float* Dv = reinterpret_cast<float*>(dSs + T16 * PP);
+  const int seq = blockIdx.x, head = blockIdx.y, lane = threadIdx.x;
   const int4 mt = meta[seq];
-  const int row0 = mt.x, t = min(mt.y, T);             // training batches are packed without prefix sharing (p = 0)
+  const int row0 = mt.x, t = min(mt.y, T);              // training batches are packed without prefix sharing (p = 0)
+  const int nt16 = (t + 15) / 16;                        // 16-row tiles of this sequence
   const size_t ld = static_cast<size_t>(3) * W;
-  for (int idx = threadIdx.x; idx < t * 64; idx += blockDim.x) {
-    const int r = idx >> 6, d = idx & 63;
-    const __nv_bfloat16* b = qkv + static_cast<size_t>(row0 + r) * ld + head * 64 + d;
-    Q[r * 65 + d] = __bfloat162float(b[0]);
-    K[r * 65 + d] = __bfloat162float(b[W]);
-    V[r * 65 + d] = __bfloat162float(b[2 * W]);
-    dO[r * 65 + d] = dout[static_cast<size_t>(row0 + r) * W + head * 64 + d];
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < t; i += blockDim.x) {  // D_i
-    float s = 0.f;
-    for (int d = 0; d < 64; ++d) s += dO[i * 65 + d] * __bfloat162float(o[static_cast<size_t>(row0 + i) * W + head * 64 + d]);
-    Dv[i] = s;
-  }
-  for (int idx = threadIdx.x; idx < t * t; idx += blockDim.x) {   // scores and dP
-    const int i = idx / t, j = idx - i * t;
-    float s = 0.f, dp = 0.f;
-    if (j <= i) {
-      for (int d = 0; d < 64; ++d) { s += Q[i * 65 + d] * K[j * 65 + d]; dp += dO[i * 65 + d] * V[j * 65 + d]; }
-      s *= 0.125f;
-    } else {
-      s = -INFINITY;
+  // ---- stage Q, K, V, dO (bf16) and D_i; 8 lanes per row, 16 bytes (8 elements) per lane ----
+  const int sub = lane & 7;
+  for (int r = lane >> 3; r < nt16 * 16; r += 4) {
+    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, d = q;
+    float dsum = 0.f;
+    if (r < t) {
+      const __nv_bfloat16* b = qkv + static_cast<size_t>(row0 + r) * ld + head * 64 + sub * 8;
+      q = *reinterpret_cast<const uint4*>(b);
+      k = *reinterpret_cast<const uint4*>(b + W);
+      v = *reinterpret_cast<const uint4*>(b + 2 * W);
+      const float* dr = dout + static_cast<size_t>(row0 + r) * W + head * 64 + sub * 8;
+      const float4 f0 = *reinterpret_cast<const float4*>(dr), f1 = *reinterpret_cast<const float4*>(dr + 4);
+      const uint4 ob = *reinterpret_cast<const uint4*>(o + static_cast<size_t>(row0 + r) * W + head * 64 + sub * 8);
+      const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ob);
+      const float2 o0 = __bfloat1622float2(o2[0]), o1 = __bfloat1622float2(o2[1]), o2f = __bfloat1622float2(o2[2]), o3 = __bfloat1622float2(o2[3]);
+      dsum = (f0.x * o0.x + f0.y * o0.y) + (f0.z * o1.x + f0.w * o1.y) + (f1.x * o2f.x + f1.y * o2f.y) + (f1.z * o3.x + f1.w * o3.y);
+      d.x = pack_bf16x2(f0.x, f0.y); d.y = pack_bf16x2(f0.z, f0.w); d.z = pack_bf16x2(f1.x, f1.y); d.w = pack_bf16x2(f1.z, f1.w);
     }
-    P[i * TP + j] = s;
-    dS[i * TP + j] = dp;
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 4);
+    *reinterpret_cast<uint4*>(Qs + r * ATTB_PITCH + sub * 8) = q;
+    *reinterpret_cast<uint4*>(Ks + r * ATTB_PITCH + sub * 8) = k;
+    *reinterpret_cast<uint4*>(Vs + r * ATTB_PITCH + sub * 8) = v;
+    *reinterpret_cast<uint4*>(dOs + r * ATTB_PITCH + sub * 8) = d;
+    if (sub == 0) Dv[r] = dsum;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < t; i += blockDim.x) {  // row softmax, then dS
-    float m = -INFINITY;
-    for (int j = 0; j <= i; ++j) m = fmaxf(m, P[i * TP + j]);
-    float l = 0.f;
-    for (int j = 0; j <= i; ++j) { const float e = expf(P[i * TP + j] - m); P[i * TP + j] = e; l += e; }
-    const float inv = 1.f / l, di = Dv[i];
-    for (int j = 0; j < t; ++j) {
-      const float pj = j <= i ? P[i * TP + j] * inv : 0.f;
-      P[i * TP + j] = pj;
-      dS[i * TP + j] = pj * (dS[i * TP + j] - di);
+  __syncwarp();
+  const uint32_t sQ = smem_u32(Qs), sK = smem_u32(Ks), sV = smem_u32(Vs), sdO = smem_u32(dOs);
+  const int g = lane >> 2, c = lane & 3;
+  // ---- pass 1: per query tile S, dP, softmax, dS, dQ; P and dS to shared memory ----
+  for (int qi = 0; qi < nt16; ++qi) {
+    float dq[8][4];
+    switch (qi) {                                          // warp-uniform
+      case 0: attb_query_tile<1>(sQ, sK, sV, sdO, Ps, dSs, Dv, PP, lane, dq); break;
+      case 1: attb_query_tile<2>(sQ, sK, sV, sdO, Ps, dSs, Dv, PP, lane, dq); break;
+      case 2: attb_query_tile<3>(sQ, sK, sV, sdO, Ps, dSs, Dv, PP, lane, dq); break;
+      case 3: attb_query_tile<4>(sQ, sK, sV, sdO, Ps, dSs, Dv, PP, lane, dq); break;
+      default: attb_query_tile<5>(sQ, sK, sV, sdO, Ps, dSs, Dv, PP, lane, dq); break;
+    }
+    const int i0 = 16 * qi + g, i1 = i0 + 8;
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) {
+      __nv_bfloat16* dst = dqkv + head * 64 + 8 * n8 + 2 * c;
+      if (i0 < t) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + i0) * ld) = pack_bf16x2(dq[n8][0], dq[n8][1]);
+      if (i1 < t) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + i1) * ld) = pack_bf16x2(dq[n8][2], dq[n8][3]);
     }
   }
-  __syncthreads();
-  for (int idx = threadIdx.x; idx < t * 64; idx += blockDim.x) {
-    const int r = idx >> 6, d = idx & 63;
-    float dq = 0.f, dk = 0.f, dv = 0.f;
-    for (int j = 0; j <= r; ++j) dq += dS[r * TP + j] * K[j * 65 + d];
-    for (int i = r; i < t; ++i) { dk += dS[i * TP + r] * Q[i * 65 + d]; dv += P[i * TP + r] * dO[i * 65 + d]; }
-    __nv_bfloat16* b = dqkv + static_cast<size_t>(row0 + r) * ld + head * 64 + d;
-    b[0] = __float2bfloat16_rn(dq * 0.125f);
-    b[W] = __float2bfloat16_rn(dk * 0.125f);
-    b[2 * W] = __float2bfloat16_rn(dv);
+  __syncwarp();
+  // ---- pass 2: per key tile dV = sum_qi P^T dO, dK = sum_qi dS^T Q over the query tiles qi >= kj ----
+  const uint32_t sP = smem_u32(Ps), sdS = smem_u32(dSs);
+  // A operand from transposed storage: matrices (i 0-7, j 0-7), (i 0-7, j 8-15), (i 8-15, j 0-7), (i 8-15, j 8-15) of the [i][j] tile
+  const int mi = lane >> 3;
+  const uint32_t at_row = static_cast<uint32_t>((lane & 7) + 8 * (mi >> 1)), at_col = static_cast<uint32_t>(8 * (mi & 1));
+  const uint32_t bt_off = static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * ATTB_PITCH + 8 * (lane >> 4)) * 2);
+  for (int kj = 0; kj < nt16; ++kj) {
+    float dv[8][4], dk[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+    for (int qi = kj; qi < nt16; ++qi) {
+      uint32_t ap[4], ads[4];
+      const uint32_t off = ((16 * qi + at_row) * PP + 16 * kj + at_col) * 2;
+      ldsm_x4_t(ap, sP + off);
+      ldsm_x4_t(ads, sdS + off);
+#pragma unroll
+      for (int nd = 0; nd < 4; ++nd) {
+        uint32_t bo[4], bq[4];
+        ldsm_x4_t(bo, sdO + bt_off + (16 * qi * ATTB_PITCH + 16 * nd) * 2);
+        ldsm_x4_t(bq, sQ + bt_off + (16 * qi * ATTB_PITCH + 16 * nd) * 2);
+        mma_bf16_16816(dv[2 * nd], ap, bo[0], bo[1]);
+        mma_bf16_16816(dv[2 * nd + 1], ap, bo[2], bo[3]);
+        mma_bf16_16816(dk[2 * nd], ads, bq[0], bq[1]);
+        mma_bf16_16816(dk[2 * nd + 1], ads, bq[2], bq[3]);
+      }
+    }
+    const int j0 = 16 * kj + g, j1 = j0 + 8;
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) {
+      __nv_bfloat16* dst = dqkv + head * 64 + 8 * n8 + 2 * c;
+      if (j0 < t) {
+        *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + j0) * ld + W) = pack_bf16x2(dk[n8][0], dk[n8][1]);
+        *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + j0) * ld + 2 * W) = pack_bf16x2(dv[n8][0], dv[n8][1]);
+      }
+      if (j1 < t) {
+        *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + j1) * ld + W) = pack_bf16x2(dk[n8][2], dk[n8][3]);
+        *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + j1) * ld + 2 * W) = pack_bf16x2(dv[n8][2], dv[n8][3]);
+      }
+    }
   }
 }
 
