@@ -811,9 +811,10 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
 }
 
 template <typename Tp>
-static int launch_transpose(leaf_engine* e, const Tp* src, __nv_bfloat16* dst, int R, int C, int Rp, cudaStream_t st) {
+static int launch_transpose(leaf_engine* e, const Tp* src, __nv_bfloat16* dst, int R, int C, int Rp, cudaStream_t st,
+                            float* colsum = nullptr) {
   dim3 grid(static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>((Rp + 31) / 32));
-  transpose_bf16_kernel<Tp><<<grid, dim3(32, 8), 0, st>>>(src, dst, R, C, Rp);
+  transpose_bf16_kernel<Tp><<<grid, dim3(32, 8), 0, st>>>(src, dst, R, C, Rp, colsum);
   e->launches++;
   CK(cudaGetLastError());
   return LEAF_OK;
@@ -831,7 +832,8 @@ static int launch_colsum(leaf_engine* e, const Tp* src, int R, int C, int ld, fl
 }
 
 static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x, const int* gather, int rows, const float* gamma,
-                                float* dx, int accumulate, float* dgamma, float* dbeta, float* scratch, cudaStream_t st) {
+                                float* dx, int accumulate, float* dgamma, float* dbeta, float* scratch, cudaStream_t st,
+                                __nv_bfloat16* dx16 = nullptr) {
   const int W = e->cfg.width;
   // frozen LayerNorm parameters (NULL grads) still need somewhere to add to: the scratch row pair
   if (!dgamma) dgamma = scratch;
@@ -839,7 +841,7 @@ static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x,
   int blocks = (rows + 7) / 8;
   if (blocks > e->sm_count) blocks = e->sm_count;
   if (blocks < 1) blocks = 1;
-#define LNB_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gather, rows, W, gamma, e->cfg.ln_eps, dx, accumulate, dgamma, dbeta); break;
+#define LNB_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gather, rows, W, gamma, e->cfg.ln_eps, dx, accumulate, dgamma, dbeta, dx16); break;
   switch (W / 128) {
     LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
     LNB_CASE(9) LNB_CASE(10) LNB_CASE(11) LNB_CASE(12) LNB_CASE(13) LNB_CASE(14) LNB_CASE(15) LNB_CASE(16)
@@ -877,9 +879,11 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
       if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(grads->text_projection), E, W, E, Np, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
     }
   }
+  // dx and its bf16 copy dx16 (the A operand of the next dgrad GEMM) are written together by the LayerNorm backward
   CK(cudaMemsetAsync(t.dx, 0, static_cast<size_t>(M) * W * 4, st));
+  CK(cudaMemsetAsync(t.dx16, 0, static_cast<size_t>(M) * W * 2, st));
   CK(cudaMemsetAsync(scratch, 0, 2 * W * 4, st));
-  if ((rc = launch_layernorm_bwd(e, t.dtmp, t.x_out, t.eos_row, N, e->wp.lnf_w, t.dx, 0, F(grads->lnf_w), F(grads->lnf_b), scratch, st))) return rc;
+  if ((rc = launch_layernorm_bwd(e, t.dtmp, t.x_out, t.eos_row, N, e->wp.lnf_w, t.dx, 0, F(grads->lnf_w), F(grads->lnf_b), scratch, st, t.dx16))) return rc;
   const size_t nx = static_cast<size_t>(M) * W;
   for (int l = e->cfg.layers - 1; l >= 0; --l) {
     const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
@@ -887,43 +891,38 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
     const LayerW& w = e->lw[l];
     TrainLayer& a = t.L[l];
     // ================= MLP branch: x_next = x_mid + fc2(act(fc1(ln_2(x_mid)))) =================
-    cast_f32_bf16_kernel<<<launch_ew(e, nx), 256, 0, st>>>(t.dx, t.dx16, nx);
-    e->launches++;
     if ((rc = launch_gemm(e, t.dx16, cap, w.fc2_wT, nullptr, t.dtmp, 4 * W, M, 4 * W, W, EPI_F32, 0, nullptr, st))) return rc;   // dg [M,4W]
     if (g.fc2_w) {
-      if ((rc = launch_transpose(e, t.dx, t.t1, M, W, Mp, st))) return rc;                                                 // dx^T [W,Mp]
+      if ((rc = launch_transpose(e, t.dx, t.t1, M, W, Mp, st, F(g.fc2_b)))) return rc;                                     // dx^T [W,Mp] (+ bias grad)
       if ((rc = launch_transpose(e, a.g, t.t2, M, 4 * W, Mp, st))) return rc;                                              // g^T [4W,Mp]
       if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(g.fc2_w), 4 * W, W, 4 * W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-    }
-    if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.fc2_b), st))) return rc;
+    } else if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.fc2_b), st))) return rc;
     const size_t nu = static_cast<size_t>(M) * 4 * W;
     act_bwd_kernel<<<launch_ew(e, nu), 256, 0, st>>>(t.dtmp, a.u, t.d16, nu, e->cfg.activation);                           // du [M,4W] bf16
     e->launches++;
     if ((rc = launch_gemm(e, t.d16, cap, w.fc1_wT, nullptr, t.dtmp, W, M, W, 4 * W, EPI_F32, 0, nullptr, st))) return rc;        // dh2 [M,W]
     if (g.fc1_w) {
-      if ((rc = launch_transpose(e, t.d16, t.t1, M, 4 * W, Mp, st))) return rc;                                            // du^T [4W,Mp]
+      if ((rc = launch_transpose(e, t.d16, t.t1, M, 4 * W, Mp, st, F(g.fc1_b)))) return rc;                                // du^T [4W,Mp] (+ bias grad)
       if ((rc = launch_transpose(e, a.h2, t.t2, M, W, Mp, st))) return rc;                                                 // h2^T [W,Mp]
       if ((rc = launch_gemm(e, t.t1, 4 * W, t.t2, nullptr, F(g.fc1_w), W, 4 * W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-    }
-    if ((rc = launch_colsum(e, t.d16, M, 4 * W, 4 * W, F(g.fc1_b), st))) return rc;
-    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_mid, nullptr, M, p.ln2_w, t.dx, 1, F(g.ln2_w), F(g.ln2_b), scratch, st))) return rc;
+    } else if ((rc = launch_colsum(e, t.d16, M, 4 * W, 4 * W, F(g.fc1_b), st))) return rc;
+    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_mid, nullptr, M, p.ln2_w, t.dx, 1, F(g.ln2_w), F(g.ln2_b), scratch, st, t.dx16))) return rc;
     // ================= attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in)))) =================
-    cast_f32_bf16_kernel<<<launch_ew(e, nx), 256, 0, st>>>(t.dx, t.dx16, nx);
-    e->launches++;
     if ((rc = launch_gemm(e, t.dx16, cap, w.out_wT, nullptr, t.dtmp, W, M, W, W, EPI_F32, 0, nullptr, st))) return rc;           // do [M,W]
     if (g.out_w) {
-      if ((rc = launch_transpose(e, t.dx, t.t1, M, W, Mp, st))) return rc;
+      if ((rc = launch_transpose(e, t.dx, t.t1, M, W, Mp, st, F(g.out_b)))) return rc;
       if ((rc = launch_transpose(e, a.o, t.t2, M, W, Mp, st))) return rc;
       if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(g.out_w), W, W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-    }
-    if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.out_b), st))) return rc;
+    } else if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.out_b), st))) return rc;
     attention_bwd_kernel<<<dim3(N, H), 32, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16);   // dqkv [M,3W] bf16
     e->launches++;
     CK(cudaGetLastError());
     if ((rc = launch_gemm(e, t.d16, cap, w.qkv_wT, nullptr, t.dtmp, W, M, W, 3 * W, EPI_F32, 0, nullptr, st))) return rc;        // dh1 [M,W]
-    const bool fused = g.in_proj_w != nullptr;
-    if (fused || g.q_w || g.k_w || g.v_w) {
-      if ((rc = launch_transpose(e, t.d16, t.t1, M, 3 * W, Mp, st))) return rc;                                            // dqkv^T [3W,Mp]
+    const bool fused = p.in_proj_w != nullptr;                                     // layout of the bound parameters
+    bool bias_done = false;
+    if (fused ? g.in_proj_w != nullptr : (g.q_w || g.k_w || g.v_w)) {
+      if ((rc = launch_transpose(e, t.d16, t.t1, M, 3 * W, Mp, st, fused ? F(g.in_proj_b) : nullptr))) return rc;          // dqkv^T [3W,Mp] (+ bias grad)
+      bias_done = fused;
       if ((rc = launch_transpose(e, a.h1, t.t2, M, W, Mp, st))) return rc;                                                 // h1^T [W,Mp]
       if (fused) {
         if ((rc = launch_gemm(e, t.t1, 3 * W, t.t2, nullptr, F(g.in_proj_w), W, 3 * W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
@@ -935,13 +934,13 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
       }
     }
     if (fused) {
-      if ((rc = launch_colsum(e, t.d16, M, 3 * W, 3 * W, F(g.in_proj_b), st))) return rc;
+      if (!bias_done && (rc = launch_colsum(e, t.d16, M, 3 * W, 3 * W, F(g.in_proj_b), st))) return rc;
     } else {
       const float* dst[3] = {g.q_b, g.k_b, g.v_b};
       for (int j = 0; j < 3; ++j)
         if ((rc = launch_colsum(e, t.d16 + j * W, M, W, 3 * W, F(dst[j]), st))) return rc;
     }
-    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_in, nullptr, M, p.ln1_w, t.dx, 1, F(g.ln1_w), F(g.ln1_b), scratch, st))) return rc;
+    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_in, nullptr, M, p.ln1_w, t.dx, 1, F(g.ln1_w), F(g.ln1_b), scratch, st, t.dx16))) return rc;
   }
   if (grads->token_embedding || grads->positional_embedding) {
     // a frozen table still needs a target for the atomics: reuse dtmp as a sink is not possible (49408 rows) -> require both

@@ -43,6 +43,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
 }
 
 // ---- dst[C, Rp] (bf16) = src[R, C]^T, rows r >= R zero-filled (Rp = R rounded up to 8: TMA row pitch) --------------
+// colsum != nullptr: colsum[c] += sum_r src[r, c] as well (the bias gradient of the Linear whose wgrad operand this is):
+// the tile is in shared memory anyway, so the separate column-sum pass over the same matrix disappears.
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>
@@ -51,7 +53,8 @@ template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 template <typename T>
-__global__ void transpose_bf16_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int Rp) {
+__global__ void transpose_bf16_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int Rp,
+                                      float* __restrict__ colsum = nullptr) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -62,6 +65,12 @@ __global__ void transpose_bf16_kernel(const T* __restrict__ src, __nv_bfloat16* 
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, r = r0 + threadIdx.x;
     if (c < C && r < Rp) dst[static_cast<size_t>(c) * Rp + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+  }
+  if (colsum && threadIdx.y == 0 && c0 + threadIdx.x < C) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s += tile[i][threadIdx.x];
+    atomicAdd(colsum + c0 + threadIdx.x, s);
   }
 }
 
@@ -90,7 +99,8 @@ template <int VPL>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                            const int* __restrict__ gather, int rows, int W,
                                                            const float* __restrict__ gamma, float eps, float* __restrict__ dx,
-                                                           int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                           int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                           __nv_bfloat16* __restrict__ dx16 = nullptr) {
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   float4 dg_acc[VPL], db_acc[VPL], g[VPL];
@@ -147,6 +157,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
       }
       out[lane + 32 * i] = o;
+      if (dx16) {                              // bf16 copy: the A operand of the next dgrad GEMM
+        uint2 pk;
+        pk.x = pack_bf16x2(o.x, o.y);
+        pk.y = pack_bf16x2(o.z, o.w);
+        reinterpret_cast<uint2*>(dx16 + static_cast<size_t>(xr) * W)[lane + 32 * i] = pk;
+      }
     }
   }
   // CTA-level reduction (warps take turns on a shared accumulator), then ONE atomic per column and CTA
