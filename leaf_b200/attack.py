@@ -82,6 +82,34 @@ def _engine_of(model) -> LeafEngine:
     raise LeafError("model must be a LeafTextTower, a LeafEngine, or a torch module in open_clip / HF CLIP naming")
 
 
+def _fast_draw(N, n):
+    """What np.random.choice(range(N), size=n, replace=n > N) returns and consumes (legacy RandomState: a prefix of
+    permutation(N) without replacement, randint with), minus choice()'s per-call overhead (26 -> 6 us; the 2 B draws of a
+    round are the whole host cost of attack_text_leaf)."""
+    return np.random.permutation(N)[:n] if n <= N else np.random.randint(0, N, size=n)
+
+
+def _fast_draw_matches_choice():
+    st = np.random.get_state()
+    try:
+        for N, n in ((7, 3), (161, 50), (96, 50), (5, 9), (1, 1)):
+            np.random.seed(12345)
+            a, ra = np.random.choice(range(N), size=n, replace=n > N), np.random.random()
+            np.random.seed(12345)
+            b, rb = _fast_draw(N, n), np.random.random()
+            if not (a.dtype == b.dtype and np.array_equal(a, b) and ra == rb):
+                return False
+        return True
+    except Exception:
+        return False
+    finally:
+        np.random.set_state(st)
+
+
+# the shortcut is used only if THIS numpy draws the same numbers and leaves the global stream in the same state
+_DRAW = _fast_draw if _fast_draw_matches_choice() else (lambda N, n: np.random.choice(range(N), size=n, replace=n > N))
+
+
 def _valid_mask(constrain, sentences, SS, B, n, device):
     """utils_attacks.py:321-325 / :360-364: candidates failing the constraint are replaced by the current sentence.
     constrain=True runs the filter on the device (engine.load_words + leaf_constrain_mask); a callable
@@ -132,20 +160,18 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
     for _ in range(k):
         lens = [len(S) for S in sentences]
         # --- host: the reference's draws for the WHOLE batch, in the reference's order (pre-drawn: SURVEY.md app. E) ---
-        positions = np.stack([np.random.choice(range(2 * L + 1), size=n, replace=n > 2 * L + 1) for L in lens])  # :317
-        us = np.stack([np.random.choice(range(len(V)), size=n, replace=(n > len(V))) for _ in sentences])       # :236
-        chars2 = Vt[us]
+        # The character draws (:236) follow the position draws (:317) in the global stream and nothing else consumes it in
+        # between, so they are made AFTER phase 1 has been queued: the host draws while the device scores.
+        positions = np.stack([_DRAW(2 * L + 1, n) for L in lens])                                                # :317
         mine = sentences[blo:bhi]
         pos_l = np.ascontiguousarray(positions[blo:bhi, jlo:jhi]).astype(np.int32)
-        chr2_l = np.ascontiguousarray(chars2[blo:bhi, jlo:jhi])
         picks = np.zeros((2, B), dtype=np.int64)                              # global candidate index per phase
         feat_l = torch.zeros((Bl, eng.embed_dim), dtype=torch.float32, device=dev)
         ok2 = np.ones(B, dtype=bool)
         if Bl > 0 and nl > 0:
             caps_d, off_d = eng.upload_captions(mine)
-            host = np.concatenate([pos_l.ravel(), np.full(Bl * nl, 32, dtype=np.int32), chr2_l.ravel()])
-            host_d = _to_dev(host, dev)
-            pos_d, chr1_d, chr2_d = host_d[:Bl * nl], host_d[Bl * nl:2 * Bl * nl], host_d[2 * Bl * nl:]
+            host_d = _to_dev(np.concatenate([pos_l.ravel(), np.full(Bl * nl, 32, dtype=np.int32)]), dev)
+            pos_d, chr1_d = host_d[:Bl * nl], host_d[Bl * nl:]
             # --- phase 1: choose the position (a space at each drawn z), :316-353 ---
             valid1 = eng.constrain_mask(caps_d, off_d, Bl, nl, pos_d, chr1_d) if on_device else None     # :321-325
             if valid_fn is not None:
@@ -154,6 +180,11 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
             tok, ln, base = eng.expand_tokenize(caps_d, off_d, Bl, nl, pos=pos_d, chr_=chr1_d, valid=valid1)
             feats = eng.encode_tokens(tok, ln, normalize, base, (Bl * nl, nl))   # rows [0, Bl*nl): candidates, then Bl captions
             best1, _, loss1 = eng.score(feats, anchor, Bl, nl, objective, want_loss=(debug or shard == "candidates"))
+        us = np.stack([_DRAW(len(V), n) for _ in sentences])                                                     # :236
+        chars2 = Vt[us]
+        chr2_l = np.ascontiguousarray(chars2[blo:bhi, jlo:jhi])
+        if Bl > 0 and nl > 0:
+            chr2_d = _to_dev(chr2_l.ravel(), dev)
         if shard == "candidates":
             val1 = loss1.gather(1, best1.long().view(-1, 1)).squeeze(1)
             _, g1 = D.cross_shard_argmax(val1, best1.long() + jlo, group)     # global index of the best position

@@ -166,3 +166,18 @@ def test_sharded_modes_equal_the_unsharded_run_gloo_world2():
     full = 2 * c["k"] * (c["B"] * c["n"] + c["B"])
     assert out[0][("samples", 1)][2] + out[1][("samples", 1)][2] == full
     assert out[0][("candidates", 1)][2] < 0.6 * full
+
+
+def test_fast_draw_is_np_random_choice():
+    """attack_text_leaf draws with permutation / randint instead of np.random.choice(range(N), n, replace=n > N): same numbers,
+    same dtype, same state of the global stream afterwards (utils_attacks.py:317, :236) - for every population size a
+    caption or the alphabet can produce."""
+    from leaf_b200 import attack
+    assert attack._DRAW is attack._fast_draw
+    for N in list(range(1, 130)) + [161, 401, 2001]:
+        for n in (1, 2, 10, 50, 200):
+            np.random.seed(N * 7 + n)
+            a, ra = np.random.choice(range(N), size=n, replace=n > N), np.random.random()
+            np.random.seed(N * 7 + n)
+            b, rb = attack._fast_draw(N, n), np.random.random()
+            assert a.dtype == b.dtype and np.array_equal(a, b) and ra == rb, (N, n)
