@@ -516,7 +516,7 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
   if (N <= 0) return fail(LEAF_ERR_INVALID, "N=%d", N);
   if (N > e->max_seqs) return fail(LEAF_ERR_STATE, "workspace reserved for %d rows, need %d (leaf_reserve)", e->max_seqs, N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int W = e->cfg.width, E = e->cfg.embed_dim, H = e->cfg.heads;
+  const int W = e->cfg.width, E = e->cfg.embed_dim;
   const int rows_max = static_cast<int>(static_cast<long>(N) * LEAF_CTX);
   int rc;
   const int* dup = nullptr;
@@ -768,7 +768,7 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
   if (N > e->tw.max_seqs) return fail(LEAF_ERR_STATE, "training workspace reserved for %d sequences, need %d (leaf_train_reserve)", e->tw.max_seqs, N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   TrainWs& t = e->tw;
-  const int W = e->cfg.width, E = e->cfg.embed_dim, H = e->cfg.heads;
+  const int W = e->cfg.width, E = e->cfg.embed_dim;
   int rc;
   t.have_forward = false;
   CK(cudaMemcpyAsync(t.tok, tok, static_cast<size_t>(N) * LEAF_CTX * 4, cudaMemcpyDeviceToDevice, st));
@@ -884,7 +884,6 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
   CK(cudaMemsetAsync(t.dx16, 0, static_cast<size_t>(M) * W * 2, st));
   CK(cudaMemsetAsync(scratch, 0, 2 * W * 4, st));
   if ((rc = launch_layernorm_bwd(e, t.dtmp, t.x_out, t.eos_row, N, e->wp.lnf_w, t.dx, 0, F(grads->lnf_w), F(grads->lnf_b), scratch, st, t.dx16))) return rc;
-  const size_t nx = static_cast<size_t>(M) * W;
   for (int l = e->cfg.layers - 1; l >= 0; --l) {
     const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
     const leaf_layer_ptrs_t& g = grads->layers[l];
