@@ -198,6 +198,10 @@ int leaf_test_layernorm(leaf_handle_t h, const float* x, int32_t rows, const flo
 /* out[rows,W] (bf16) = causal attention over packed qkv[rows,3W] (bf16); meta [N,4] int32 = {own_row, t, p, base_row}
  * per sequence (positions [p,t) are rows own_row.., keys/values of [0,p) are rows base_row..). */
 int leaf_test_attention(leaf_handle_t h, const void* qkv, const int32_t* meta, int32_t N, void* out, void* stream);
+/* K4's attention backward alone: qkv [rows,3W] bf16, o [rows,W] bf16 (the forward output), dout [rows,W] fp32, meta as above
+ * with p = 0 (training batches share no prefixes), T >= the longest sequence; dqkv [rows,3W] bf16 = (dQ | dK | dV). */
+int leaf_test_attention_bwd(leaf_handle_t h, const void* qkv, const void* o, const float* dout, const int32_t* meta, int32_t N,
+                            int32_t T, void* dqkv, void* stream);
 /* leaf_encode computes the final layer's out-proj / LayerNorm / MLP on the pooled EOS row of every sequence only (the
  * one row transformer.py:661 reads); on by default, results are bit-identical either way. on = 0 computes every row. */
 int leaf_set_prune_last(leaf_handle_t h, int32_t on);

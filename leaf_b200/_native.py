@@ -55,6 +55,7 @@ SIGNATURES = {
                                c_void_p, c_void_p]),
     "leaf_test_layernorm": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "leaf_test_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
+    "leaf_test_attention_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "leaf_set_prune_last": (c_int, [c_void_p, c_int]),
     "leaf_launch_count": (c_i64, [c_void_p, c_int]),
     "leaf_last_rows": (c_i64, [c_void_p]),

@@ -628,6 +628,17 @@ extern "C" int leaf_test_attention(leaf_handle_t e, const void* qkv, const int32
                           static_cast<__nv_bfloat16*>(out), 0, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int leaf_test_attention_bwd(leaf_handle_t e, const void* qkv, const void* o, const float* dout, const int32_t* meta,
+                                       int32_t N, int32_t T, void* dqkv, void* stream) {
+  if (!e || !qkv || !o || !dout || !meta || !dqkv || N <= 0 || T <= 0 || T > LEAF_CTX) return fail(LEAF_ERR_INVALID, "bad argument");
+  attention_bwd_kernel<<<dim3(N, e->cfg.heads), 32, attb_smem_bytes(T), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(o), dout, reinterpret_cast<const int4*>(meta),
+      e->cfg.width, T, static_cast<__nv_bfloat16*>(dqkv));
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
 extern "C" int leaf_set_prune_last(leaf_handle_t e, int32_t on) {
   if (!e) return fail(LEAF_ERR_INVALID, "null handle");
   e->prune_last = on != 0;

@@ -378,6 +378,13 @@ class LeafEngine:
         check(self._lib.leaf_test_attention(self._h, _ptr(qkv), _ptr(meta), meta.shape[0], _ptr(out), _stream()))
         return out
 
+    def test_attention_bwd(self, qkv, o, dout, meta, T):
+        """K4's attention backward alone: dqkv bf16 [rows, 3W] = (dQ | dK | dV); meta as test_attention with p = 0."""
+        dqkv = torch.zeros_like(qkv)
+        check(self._lib.leaf_test_attention_bwd(self._h, _ptr(qkv), _ptr(o), _ptr(dout), _ptr(meta), meta.shape[0], int(T),
+                                                _ptr(dqkv), _stream()))
+        return dqkv
+
     def set_prune_last(self, on: bool):
         """Final-layer pruning (out-proj / MLP on the pooled EOS rows only); on by default, bit-identical either way."""
         check(self._lib.leaf_set_prune_last(self._h, 1 if on else 0))

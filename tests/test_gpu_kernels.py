@@ -111,6 +111,37 @@ def test_attention_varlen_causal(eng):
         assert torch.allclose(out[t0:], ref_attn(q[p:], k, v, p), atol=3e-2, rtol=2e-2), p
 
 
+def test_attention_backward_kernel(eng):
+    """K4's tensor-core attention backward against torch autograd of an fp32 attention on the same bf16 inputs: every
+    length class (1 row, tile boundaries 16 / 17 / 32 / 33, the full 77)."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    W, H = eng.width, eng.heads
+    lens = [1, 2, 13, 77, 40, 5, 16, 17, 32, 33, 64, 65]
+    cu = np.concatenate([[0], np.cumsum(lens)])
+    rows = int(cu[-1])
+    qkv = (0.7 * torch.randn((rows, 3 * W), generator=g, device="cuda")).to(torch.bfloat16)
+    dout = torch.randn((rows, W), generator=g, device="cuda")
+    meta = torch.tensor([[cu[i], t, 0, cu[i]] for i, t in enumerate(lens)], dtype=torch.int32, device="cuda")
+    o = eng.test_attention(qkv, meta)
+    want = torch.zeros((rows, 3 * W), device="cuda")
+    for i, t in enumerate(lens):
+        s = int(cu[i])
+        x = qkv[s:s + t].float().requires_grad_(True)
+        q, k, v = (z.view(t, H, 64).transpose(0, 1) for z in x.split(W, dim=-1))
+        mask = torch.full((t, t), float("-inf"), device="cuda").triu_(1)
+        out = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125 + mask, -1) @ v).transpose(0, 1).reshape(t, W)
+        out.backward(dout[s:s + t])
+        want[s:s + t] = x.grad
+    for T in (77,):
+        got = eng.test_attention_bwd(qkv, o, dout, meta, T).float()
+        for name, sl in (("dq", slice(0, W)), ("dk", slice(W, 2 * W)), ("dv", slice(2 * W, 3 * W))):
+            a, b = got[:, sl], want[:, sl]
+            rel = ((a - b).norm() / b.norm()).item()
+            # P, dS and dO enter the products as bf16 and the result is stored as bf16
+            assert rel < 1.5e-2, (name, T, rel)
+            assert torch.allclose(a, b, atol=6e-2, rtol=6e-2), (name, T, (a - b).abs().max().item())
+
+
 def test_score_argmax(eng):
     g = torch.Generator(device="cuda").manual_seed(3)
     E = eng.embed_dim
