@@ -192,6 +192,11 @@ int leaf_sumsq(leaf_handle_t h, const float* g, int64_t n, float* out, void* str
 int leaf_gemm_bf16(leaf_handle_t h, const void* A, const void* Bt, const float* bias, void* C,
                    int32_t M, int32_t N, int32_t K, int32_t epilogue, int32_t act, const int32_t* m_dev,
                    void* stream);
+/* The same kernel with MN-major operands: B is [K,N] row-major; A is [K,M] row-major when a_mn != 0 (C = A^T . B, the shape
+ * of a weight gradient dW[out,in] = dY[rows,out]^T . X[rows,in], read as the activations lie), else [M,K] (C = A . B, the
+ * shape of a data gradient dX = dY . W with W [out,in] as it lies). M (when a_mn) and N multiples of 8; epilogue as above. */
+int leaf_gemm_bf16_mn(leaf_handle_t h, const void* A, const void* B, const float* bias, void* C, int32_t M, int32_t N,
+                      int32_t K, int32_t epilogue, int32_t a_mn, void* stream);
 /* y[rows,W] (bf16) = LayerNorm(x[rows,W] fp32) with the tower's kernel; W = cfg.width. */
 int leaf_test_layernorm(leaf_handle_t h, const float* x, int32_t rows, const float* gamma, const float* beta, void* y,
                         void* stream);

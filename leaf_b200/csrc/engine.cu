@@ -50,7 +50,6 @@ typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 
 struct LayerW {
   __nv_bfloat16 *qkv_w = nullptr, *out_w = nullptr, *fc1_w = nullptr, *fc2_w = nullptr;   // engine-owned bf16 copies
-  __nv_bfloat16 *qkv_wT = nullptr, *out_wT = nullptr, *fc1_wT = nullptr, *fc2_wT = nullptr;   // [in,out] copies for dgrad (K4)
   float* qkv_b_own = nullptr;                                                              // HF layout only
   const float* qkv_b = nullptr;
 };
@@ -67,7 +66,7 @@ struct TrainWs {
   bool have_forward = false;
   std::vector<TrainLayer> L;
   float *x_out = nullptr, *dx = nullptr, *dtmp = nullptr, *scratch = nullptr;
-  __nv_bfloat16 *pooled = nullptr, *d16 = nullptr, *dx16 = nullptr, *t1 = nullptr, *t2 = nullptr;
+  __nv_bfloat16 *pooled = nullptr, *d16 = nullptr, *dx16 = nullptr;
   int *tok = nullptr, *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr;
   int4* meta = nullptr;
   std::vector<void*> allocs;
@@ -94,8 +93,6 @@ struct leaf_engine {
   std::vector<leaf_layer_ptrs_t> layer_ptrs;
   std::vector<LayerW> lw;
   __nv_bfloat16* proj_w = nullptr;    // [E, W] bf16
-  __nv_bfloat16* proj_wT = nullptr;   // [W, E] bf16 (training: dgrad of the projection)
-  bool train_weights = false;         // transposed bf16 copies (dgrad operands) are kept
   TrainWs tw;
   // workspace
   int max_seqs = 0;
@@ -145,6 +142,29 @@ static int make_tmap(leaf_engine* e, const void* ptr, long rows, long cols, int 
   return LEAF_OK;
 }
 
+// operand stored [k_rows, mn_cols] row-major (MN-major): boxes of 64 MN elements (one 128-byte swizzle row) x 64 k
+static int make_tmap_mn(leaf_engine* e, const void* ptr, long k_rows, long mn_cols, long pitch, CUtensorMap* out) {
+  if (pitch <= 0) pitch = mn_cols;
+  auto key = std::make_tuple(ptr, k_rows, mn_cols, -static_cast<int>(pitch));
+  auto it = e->tmaps.find(key);
+  if (it != e->tmaps.end()) { *out = it->second; return LEAF_OK; }
+  if (mn_cols % 8 != 0 || pitch % 8 != 0) return fail(LEAF_ERR_INVALID, "MN-major operand width (%ld) and pitch (%ld) must be multiples of 8", mn_cols, pitch);
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return fail(LEAF_ERR_INVALID, "GEMM operand must be 16-byte aligned");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(mn_cols), static_cast<cuuint64_t>(k_rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch) * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = e->encode_tiled(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LEAF_ERR_CUDA, "cuTensorMapEncodeTiled (MN-major) failed (%d) rows=%ld cols=%ld", (int)r, k_rows, mn_cols);
+  if (e->tmaps.size() > 4096) e->tmaps.clear();
+  e->tmaps[key] = m;
+  *out = m;
+  return LEAF_OK;
+}
+
 static cudaEvent_t get_event(leaf_engine* e) {
   if (!e->event_pool.empty()) { cudaEvent_t ev = e->event_pool.back(); e->event_pool.pop_back(); return ev; }
   cudaEvent_t ev;
@@ -166,17 +186,24 @@ struct TimedSpan {
 // C[M,N] = A[M,K] . Bt[N,K]^T with the fused epilogue `epi`
 static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, const __nv_bfloat16* Bt, const float* bias,
                        void* C, int ldc, int M, int N, int K, int epi, int act, const int* m_dev, cudaStream_t st,
-                       const __nv_bfloat16* delta = nullptr) {
+                       const __nv_bfloat16* delta = nullptr, int mn_major = 0, long a_pitch = 0) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(LEAF_ERR_INVALID, "GEMM shape %dx%dx%d", M, N, K);
   if (N % 8 != 0) return fail(LEAF_ERR_INVALID, "GEMM N (%d) must be a multiple of 8", N);
   CUtensorMap ta, tb;
-  const int a_box = a_rows < 128 ? static_cast<int>(a_rows) : 128;
-  const int b_box = N < 128 ? N : 128;
-  int rc = make_tmap(e, A, a_rows, K, a_box, &ta);
-  if (rc) return rc;
-  rc = make_tmap(e, Bt, N, K, b_box, &tb);
-  if (rc) return rc;
+  int a_box = a_rows < 128 ? static_cast<int>(a_rows) : 128;
+  int b_box = N < 128 ? N : 128;
+  int rc;
+  if (mn_major & GEMM_A_MN) {                  // A is [K, M] row-major
+    if (M % 8 != 0) return fail(LEAF_ERR_INVALID, "MN-major GEMM M (%d) must be a multiple of 8", M);
+    if ((rc = make_tmap_mn(e, A, K, M, a_pitch, &ta))) return rc;      // a_pitch: row pitch when A is a column block of a wider matrix
+    a_box = 128;
+  } else if ((rc = make_tmap(e, A, a_rows, K, a_box, &ta))) return rc;
+  if (mn_major & GEMM_B_MN) {                  // Bt is [K, N] row-major
+    if ((rc = make_tmap_mn(e, Bt, K, N, 0, &tb))) return rc;
+    b_box = 128;
+  } else if ((rc = make_tmap(e, Bt, N, K, b_box, &tb))) return rc;
   GemmParams p;
+  p.mn_major = mn_major;
   p.tx_bytes = static_cast<uint32_t>(a_box + b_box) * GEMM_BK * 2 * 2;       // both CTAs of the pair
   p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act; p.delta = delta;
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
@@ -255,12 +282,10 @@ static void free_workspace(leaf_engine* e) {
 static void free_weights(leaf_engine* e) {
   for (auto& l : e->lw) {
     cudaFree(l.qkv_w); cudaFree(l.out_w); cudaFree(l.fc1_w); cudaFree(l.fc2_w); cudaFree(l.qkv_b_own);
-    cudaFree(l.qkv_wT); cudaFree(l.out_wT); cudaFree(l.fc1_wT); cudaFree(l.fc2_wT);
   }
   e->lw.clear();
-  cudaFree(e->proj_w); cudaFree(e->proj_wT);
-  e->proj_w = e->proj_wT = nullptr;
-  e->train_weights = false;
+  cudaFree(e->proj_w);
+  e->proj_w = nullptr;
   e->bound = false;
   e->tmaps.clear();
 }
@@ -324,45 +349,6 @@ static int cast_to(leaf_engine* e, const float* src, __nv_bfloat16* dst, size_t 
   return LEAF_OK;
 }
 
-static int cast_transpose_to(leaf_engine* e, const float* src, __nv_bfloat16* dst, int R, int C, cudaStream_t st) {
-  dim3 grid(static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>((R + 31) / 32));
-  cast_bf16_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(src, dst, R, C);
-  e->launches++;
-  CK(cudaGetLastError());
-  return LEAF_OK;
-}
-
-// [in,out] bf16 copies of the Linear weights: the K-major B operand of the dgrad products dX = dY . W
-static int refresh_transposed(leaf_engine* e, cudaStream_t st) {
-  const int W = e->cfg.width, E = e->cfg.embed_dim;
-  int rc;
-  for (int l = 0; l < e->cfg.layers; ++l) {
-    const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
-    LayerW& w = e->lw[l];
-    if (p.in_proj_w) {
-      if ((rc = cast_transpose_to(e, p.in_proj_w, w.qkv_wT, 3 * W, W, st))) return rc;       // [3W,W] -> [W,3W]
-    } else {                                                                                  // three [W,W] blocks side by side
-      const float* src[3] = {p.q_w, p.k_w, p.v_w};
-      for (int j = 0; j < 3; ++j) {
-        dim3 grid(static_cast<unsigned>((W + 31) / 32), static_cast<unsigned>((W + 31) / 32));
-        cast_bf16_transpose_ld_kernel<<<grid, dim3(32, 8), 0, st>>>(src[j], w.qkv_wT + j * W, W, W, 3 * W);
-        e->launches++;
-      }
-    }
-    if ((rc = cast_transpose_to(e, p.out_w, w.out_wT, W, W, st))) return rc;
-    if ((rc = cast_transpose_to(e, p.fc1_w, w.fc1_wT, 4 * W, W, st))) return rc;             // [4W,W] -> [W,4W]
-    if ((rc = cast_transpose_to(e, p.fc2_w, w.fc2_wT, W, 4 * W, st))) return rc;             // [W,4W] -> [4W,W]
-  }
-  // dpooled[N,W] = dfeat[N,E] . P^T  =>  Bt = P as [W,E]
-  if (e->wp.projection_is_ew) {
-    if ((rc = cast_transpose_to(e, e->wp.text_projection, e->proj_wT, E, W, st))) return rc;
-  } else {
-    if ((rc = cast_to(e, e->wp.text_projection, e->proj_wT, static_cast<size_t>(W) * E, st))) return rc;
-  }
-  CK(cudaGetLastError());
-  return LEAF_OK;
-}
-
 extern "C" int leaf_refresh_weights(leaf_handle_t e, void* stream) {
   if (!e || !e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -387,9 +373,6 @@ extern "C" int leaf_refresh_weights(leaf_handle_t e, void* stream) {
     if ((rc = cast_to(e, p.out_w, w.out_w, W * W, st))) return rc;
     if ((rc = cast_to(e, p.fc1_w, w.fc1_w, 4 * W * W, st))) return rc;
     if ((rc = cast_to(e, p.fc2_w, w.fc2_w, 4 * W * W, st))) return rc;
-  }
-  if (e->train_weights) {
-    if ((rc = refresh_transposed(e, st))) return rc;
   }
   if (e->wp.projection_is_ew) {
     if ((rc = cast_to(e, e->wp.text_projection, e->proj_w, E * W, st))) return rc;
@@ -616,6 +599,13 @@ extern "C" int leaf_gemm_bf16(leaf_handle_t e, const void* A, const void* Bt, co
                      epilogue, act, m_dev, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int leaf_gemm_bf16_mn(leaf_handle_t e, const void* A, const void* B, const float* bias, void* C, int32_t M, int32_t N,
+                                 int32_t K, int32_t epilogue, int32_t a_mn, void* stream) {
+  if (!e || !A || !B || !C) return fail(LEAF_ERR_INVALID, "null argument");
+  return launch_gemm(e, static_cast<const __nv_bfloat16*>(A), a_mn ? K : M, static_cast<const __nv_bfloat16*>(B), bias, C, N, M, N, K,
+                     epilogue, 0, nullptr, static_cast<cudaStream_t>(stream), nullptr, GEMM_B_MN | (a_mn ? GEMM_A_MN : 0));
+}
+
 extern "C" int leaf_test_layernorm(leaf_handle_t e, const float* x, int32_t rows, const float* gamma, const float* beta, void* y,
                                    void* stream) {
   if (!e || !x || !gamma || !beta || !y || rows <= 0) return fail(LEAF_ERR_INVALID, "bad argument");
@@ -717,18 +707,6 @@ extern "C" int leaf_train_reserve(leaf_handle_t e, int32_t max_seqs) {
   if (!e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
   const size_t W = e->cfg.width, E = e->cfg.embed_dim;
   int rc;
-  if (!e->train_weights) {
-    for (auto& l : e->lw) {
-      CK(cudaMalloc(&l.qkv_wT, 3 * W * W * 2));
-      CK(cudaMalloc(&l.out_wT, W * W * 2));
-      CK(cudaMalloc(&l.fc1_wT, 4 * W * W * 2));
-      CK(cudaMalloc(&l.fc2_wT, 4 * W * W * 2));
-    }
-    CK(cudaMalloc(&e->proj_wT, W * E * 2));
-    e->train_weights = true;
-    if ((rc = refresh_transposed(e, nullptr))) return rc;
-    CK(cudaDeviceSynchronize());
-  }
   if (max_seqs <= e->tw.max_seqs) return LEAF_OK;
   cudaDeviceSynchronize();
   free_train(e);
@@ -753,8 +731,6 @@ extern "C" int leaf_train_reserve(leaf_handle_t e, int32_t max_seqs) {
   if ((rc = tw_alloc(t, &t.pooled, (static_cast<size_t>(max_seqs) + 128) * W))) return rc;
   if ((rc = tw_alloc(t, &t.d16, rows * wide))) return rc;
   if ((rc = tw_alloc(t, &t.dx16, rows * W))) return rc;
-  if ((rc = tw_alloc(t, &t.t1, wide * rows))) return rc;
-  if ((rc = tw_alloc(t, &t.t2, wide * rows))) return rc;
   if ((rc = tw_alloc(t, &t.tok, static_cast<size_t>(max_seqs) * LEAF_CTX))) return rc;
   if ((rc = tw_alloc(t, &t.cu, static_cast<size_t>(max_seqs) + 1))) return rc;
   if ((rc = tw_alloc(t, &t.eos_row, static_cast<size_t>(max_seqs)))) return rc;
@@ -822,16 +798,6 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
 }
 
 template <typename Tp>
-static int launch_transpose(leaf_engine* e, const Tp* src, __nv_bfloat16* dst, int R, int C, int Rp, cudaStream_t st,
-                            float* colsum = nullptr) {
-  dim3 grid(static_cast<unsigned>((C + 31) / 32), static_cast<unsigned>((Rp + 31) / 32));
-  transpose_bf16_kernel<Tp><<<grid, dim3(32, 8), 0, st>>>(src, dst, R, C, Rp, colsum);
-  e->launches++;
-  CK(cudaGetLastError());
-  return LEAF_OK;
-}
-
-template <typename Tp>
 static int launch_colsum(leaf_engine* e, const Tp* src, int R, int C, int ld, float* dst, cudaStream_t st) {
   if (!dst) return LEAF_OK;
   int gy = (R + 255) / 256;
@@ -844,7 +810,7 @@ static int launch_colsum(leaf_engine* e, const Tp* src, int R, int C, int ld, fl
 
 static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x, const int* gather, int rows, const float* gamma,
                                 float* dx, int accumulate, float* dgamma, float* dbeta, float* scratch, cudaStream_t st,
-                                __nv_bfloat16* dx16 = nullptr) {
+                                __nv_bfloat16* dx16 = nullptr, float* dxsum = nullptr) {
   const int W = e->cfg.width;
   // frozen LayerNorm parameters (NULL grads) still need somewhere to add to: the scratch row pair
   if (!dgamma) dgamma = scratch;
@@ -852,7 +818,7 @@ static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x,
   int blocks = (rows + 7) / 8;
   if (blocks > e->sm_count) blocks = e->sm_count;
   if (blocks < 1) blocks = 1;
-#define LNB_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gather, rows, W, gamma, e->cfg.ln_eps, dx, accumulate, dgamma, dbeta, dx16); break;
+#define LNB_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gather, rows, W, gamma, e->cfg.ln_eps, dx, accumulate, dgamma, dbeta, dx16, dxsum); break;
   switch (W / 128) {
     LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
     LNB_CASE(9) LNB_CASE(10) LNB_CASE(11) LNB_CASE(12) LNB_CASE(13) LNB_CASE(14) LNB_CASE(15) LNB_CASE(16)
@@ -870,87 +836,78 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
   TrainWs& t = e->tw;
   if (!t.have_forward) return fail(LEAF_ERR_STATE, "leaf_backward needs a preceding leaf_forward_train");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int W = e->cfg.width, E = e->cfg.embed_dim, H = e->cfg.heads, N = t.N, M = t.M;
-  const int Mp = (M + 7) & ~7, Np = (N + 7) & ~7;
+  const int W = e->cfg.width, E = e->cfg.embed_dim, N = t.N, M = t.M;
   const long cap = t.rows_cap;
   int rc;
   auto F = [](const float* p) { return const_cast<float*>(p); };
   float* scratch = t.scratch;                        // sink for the LayerNorm gradients of frozen parameters
+  // Every product reads its operands as they lie (MN-major UMMA operands, gemm_sm100.cuh): the data gradients take the
+  // forward's bf16 weight copy W[out,in] as B[k = out][n = in], the weight gradients take dY[rows,out] and X[rows,in] as
+  // A[k = rows][m = out] and B[k = rows][n = in]. No transposed copies of weights or activations exist.
+  auto dgrad = [&](const __nv_bfloat16* dy, long dy_rows, const __nv_bfloat16* w_oi, float* dx_out, int rows, int in, int out) {
+    return launch_gemm(e, dy, dy_rows, w_oi, nullptr, dx_out, in, rows, in, out, EPI_F32, 0, nullptr, st, nullptr, GEMM_B_MN);
+  };
+  auto wgrad = [&](const __nv_bfloat16* dy, long dy_pitch, const __nv_bfloat16* x, float* dw, int rows, int in, int out) {
+    return launch_gemm(e, dy, rows, x, nullptr, dw, in, out, in, rows, EPI_F32_RESIDUAL, 0, nullptr, st, nullptr,
+                       GEMM_A_MN | GEMM_B_MN, dy_pitch);
+  };
   // ---- projection + ln_final on the pooled rows ----
   const size_t nfe = static_cast<size_t>(N) * E;
   cast_f32_bf16_kernel<<<launch_ew(e, nfe), 256, 0, st>>>(dfeat, t.d16, nfe);
   e->launches++;
-  if ((rc = launch_gemm(e, t.d16, N, e->proj_wT, nullptr, t.dtmp, W, N, W, E, EPI_F32, 0, nullptr, st))) return rc;      // dpooled [N,W]
+  if ((rc = dgrad(t.d16, N, e->proj_w, t.dtmp, N, W, E))) return rc;                                        // dpooled [N,W] = dfeat . P[E,W]
   if (grads->text_projection) {
-    if ((rc = launch_transpose(e, t.pooled, t.t1, N, W, Np, st))) return rc;                                             // pooled^T [W,Np]
-    if ((rc = launch_transpose(e, dfeat, t.t2, N, E, Np, st))) return rc;                                                // dfeat^T  [E,Np]
     if (grads->projection_is_ew) {
-      if ((rc = launch_gemm(e, t.t2, E, t.t1, nullptr, F(grads->text_projection), W, E, W, Np, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-    } else {
-      if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(grads->text_projection), E, W, E, Np, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-    }
+      if ((rc = wgrad(t.d16, 0, t.pooled, F(grads->text_projection), N, W, E))) return rc;                 // dP[E,W] += dfeat^T . pooled
+    } else if ((rc = launch_gemm(e, t.pooled, N, t.d16, nullptr, F(grads->text_projection), E, W, E, N, EPI_F32_RESIDUAL, 0, nullptr, st,
+                                 nullptr, GEMM_A_MN | GEMM_B_MN))) return rc;                              // dP[W,E] += pooled^T . dfeat
   }
   // dx and its bf16 copy dx16 (the A operand of the next dgrad GEMM) are written together by the LayerNorm backward
   CK(cudaMemsetAsync(t.dx, 0, static_cast<size_t>(M) * W * 4, st));
   CK(cudaMemsetAsync(t.dx16, 0, static_cast<size_t>(M) * W * 2, st));
   CK(cudaMemsetAsync(scratch, 0, 2 * W * 4, st));
-  if ((rc = launch_layernorm_bwd(e, t.dtmp, t.x_out, t.eos_row, N, e->wp.lnf_w, t.dx, 0, F(grads->lnf_w), F(grads->lnf_b), scratch, st, t.dx16))) return rc;
+  // the bias gradients that are column sums of dx (fc2's, out-proj's) are accumulated by the LayerNorm backward that writes
+  // that dx: ln_final / the layer above's ln_1 for fc2, this layer's ln_2 for out-proj
+  if ((rc = launch_layernorm_bwd(e, t.dtmp, t.x_out, t.eos_row, N, e->wp.lnf_w, t.dx, 0, F(grads->lnf_w), F(grads->lnf_b), scratch, st, t.dx16,
+                                 F(grads->layers[e->cfg.layers - 1].fc2_b)))) return rc;
   for (int l = e->cfg.layers - 1; l >= 0; --l) {
     const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
     const leaf_layer_ptrs_t& g = grads->layers[l];
     const LayerW& w = e->lw[l];
     TrainLayer& a = t.L[l];
     // ================= MLP branch: x_next = x_mid + fc2(act(fc1(ln_2(x_mid)))) =================
-    if ((rc = launch_gemm(e, t.dx16, cap, w.fc2_wT, nullptr, t.dtmp, 4 * W, M, 4 * W, W, EPI_F32, 0, nullptr, st))) return rc;   // dg [M,4W]
-    if (g.fc2_w) {
-      if ((rc = launch_transpose(e, t.dx, t.t1, M, W, Mp, st, F(g.fc2_b)))) return rc;                                     // dx^T [W,Mp] (+ bias grad)
-      if ((rc = launch_transpose(e, a.g, t.t2, M, 4 * W, Mp, st))) return rc;                                              // g^T [4W,Mp]
-      if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(g.fc2_w), 4 * W, W, 4 * W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-    } else if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.fc2_b), st))) return rc;
-    const size_t nu = static_cast<size_t>(M) * 4 * W;
-    act_bwd_kernel<<<launch_ew(e, nu), 256, 0, st>>>(t.dtmp, a.u, t.d16, nu, e->cfg.activation);                           // du [M,4W] bf16
-    e->launches++;
-    if ((rc = launch_gemm(e, t.d16, cap, w.fc1_wT, nullptr, t.dtmp, W, M, W, 4 * W, EPI_F32, 0, nullptr, st))) return rc;        // dh2 [M,W]
-    if (g.fc1_w) {
-      if ((rc = launch_transpose(e, t.d16, t.t1, M, 4 * W, Mp, st, F(g.fc1_b)))) return rc;                                // du^T [4W,Mp] (+ bias grad)
-      if ((rc = launch_transpose(e, a.h2, t.t2, M, W, Mp, st))) return rc;                                                 // h2^T [W,Mp]
-      if ((rc = launch_gemm(e, t.t1, 4 * W, t.t2, nullptr, F(g.fc1_w), W, 4 * W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-    } else if ((rc = launch_colsum(e, t.d16, M, 4 * W, 4 * W, F(g.fc1_b), st))) return rc;
-    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_mid, nullptr, M, p.ln2_w, t.dx, 1, F(g.ln2_w), F(g.ln2_b), scratch, st, t.dx16))) return rc;
+    if ((rc = dgrad(t.dx16, cap, w.fc2_w, t.dtmp, M, 4 * W, W))) return rc;                                 // dg [M,4W]
+    if (g.fc2_w && (rc = wgrad(t.dx16, 0, a.g, F(g.fc2_w), M, 4 * W, W))) return rc;
+    {
+      const int cb = (4 * W + 255) / 256;
+      int bands = (e->sm_count * 4 + cb - 1) / cb;
+      if (bands > M) bands = M;
+      act_bwd_kernel<<<dim3(cb, bands), 256, 0, st>>>(t.dtmp, a.u, t.d16, M, 4 * W, e->cfg.activation, F(g.fc1_b));   // du [M,4W] bf16 (+ fc1 bias grad)
+      e->launches++;
+    }
+    if ((rc = dgrad(t.d16, cap, w.fc1_w, t.dtmp, M, W, 4 * W))) return rc;                                  // dh2 [M,W]
+    if (g.fc1_w && (rc = wgrad(t.d16, 0, a.h2, F(g.fc1_w), M, W, 4 * W))) return rc;
+    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_mid, nullptr, M, p.ln2_w, t.dx, 1, F(g.ln2_w), F(g.ln2_b), scratch, st, t.dx16, F(g.out_b)))) return rc;
     // ================= attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in)))) =================
-    if ((rc = launch_gemm(e, t.dx16, cap, w.out_wT, nullptr, t.dtmp, W, M, W, W, EPI_F32, 0, nullptr, st))) return rc;           // do [M,W]
-    if (g.out_w) {
-      if ((rc = launch_transpose(e, t.dx, t.t1, M, W, Mp, st, F(g.out_b)))) return rc;
-      if ((rc = launch_transpose(e, a.o, t.t2, M, W, Mp, st))) return rc;
-      if ((rc = launch_gemm(e, t.t1, W, t.t2, nullptr, F(g.out_w), W, W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-    } else if ((rc = launch_colsum(e, t.dx, M, W, W, F(g.out_b), st))) return rc;
-    attention_bwd_kernel<<<dim3(N, H), 32, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16);   // dqkv [M,3W] bf16
+    if ((rc = dgrad(t.dx16, cap, w.out_w, t.dtmp, M, W, W))) return rc;                                     // do [M,W]
+    if (g.out_w && (rc = wgrad(t.dx16, 0, a.o, F(g.out_w), M, W, W))) return rc;
+    attention_bwd_kernel<<<dim3(N, e->cfg.heads), 32, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16);   // dqkv [M,3W] bf16
     e->launches++;
     CK(cudaGetLastError());
-    if ((rc = launch_gemm(e, t.d16, cap, w.qkv_wT, nullptr, t.dtmp, W, M, W, 3 * W, EPI_F32, 0, nullptr, st))) return rc;        // dh1 [M,W]
-    const bool fused = p.in_proj_w != nullptr;                                     // layout of the bound parameters
-    bool bias_done = false;
-    if (fused ? g.in_proj_w != nullptr : (g.q_w || g.k_w || g.v_w)) {
-      if ((rc = launch_transpose(e, t.d16, t.t1, M, 3 * W, Mp, st, fused ? F(g.in_proj_b) : nullptr))) return rc;          // dqkv^T [3W,Mp] (+ bias grad)
-      bias_done = fused;
-      if ((rc = launch_transpose(e, a.h1, t.t2, M, W, Mp, st))) return rc;                                                 // h1^T [W,Mp]
-      if (fused) {
-        if ((rc = launch_gemm(e, t.t1, 3 * W, t.t2, nullptr, F(g.in_proj_w), W, 3 * W, W, Mp, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
-      } else {
-        const float* dst[3] = {g.q_w, g.k_w, g.v_w};
-        for (int j = 0; j < 3; ++j)
-          if (dst[j] && (rc = launch_gemm(e, t.t1 + static_cast<size_t>(j) * W * Mp, W, t.t2, nullptr, F(dst[j]), W, W, W, Mp,
-                                          EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    if ((rc = dgrad(t.d16, cap, w.qkv_w, t.dtmp, M, W, 3 * W))) return rc;                                  // dh1 [M,W]
+    if (p.in_proj_w) {                                                                                       // layout of the bound parameters
+      if (g.in_proj_w && (rc = wgrad(t.d16, 0, a.h1, F(g.in_proj_w), M, W, 3 * W))) return rc;
+      if ((rc = launch_colsum(e, t.d16, M, 3 * W, 3 * W, F(g.in_proj_b), st))) return rc;
+    } else {                                                                                                 // HF: q, k, v are column blocks of dqkv
+      const float* dw[3] = {g.q_w, g.k_w, g.v_w};
+      const float* db[3] = {g.q_b, g.k_b, g.v_b};
+      for (int j = 0; j < 3; ++j) {
+        if (dw[j] && (rc = wgrad(t.d16 + j * W, 3 * W, a.h1, F(dw[j]), M, W, W))) return rc;
+        if ((rc = launch_colsum(e, t.d16 + j * W, M, W, 3 * W, F(db[j]), st))) return rc;
       }
     }
-    if (fused) {
-      if (!bias_done && (rc = launch_colsum(e, t.d16, M, 3 * W, 3 * W, F(g.in_proj_b), st))) return rc;
-    } else {
-      const float* dst[3] = {g.q_b, g.k_b, g.v_b};
-      for (int j = 0; j < 3; ++j)
-        if ((rc = launch_colsum(e, t.d16 + j * W, M, W, 3 * W, F(dst[j]), st))) return rc;
-    }
-    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_in, nullptr, M, p.ln1_w, t.dx, 1, F(g.ln1_w), F(g.ln1_b), scratch, st, t.dx16))) return rc;
+    if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_in, nullptr, M, p.ln1_w, t.dx, 1, F(g.ln1_w), F(g.ln1_b), scratch, st, t.dx16,
+                                   l > 0 ? F(grads->layers[l - 1].fc2_b) : nullptr))) return rc;
   }
   if (grads->token_embedding || grads->positional_embedding) {
     // a frozen table still needs a target for the atomics: reuse dtmp as a sink is not possible (49408 rows) -> require both

@@ -144,8 +144,18 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const uint32_t sa = smem_base + stage * GEMM2_STAGE_BYTES;
           const uint32_t fb = full_bar(stage) & PEER_BIT_MASK;
           if (leader) mbar_arrive_expect_tx(full_bar(stage), p.tx_bytes);
-          tma_load_2d_2sm(sa, &tmap_a, fb, kb * GEMM_BK, a_row);
-          tma_load_2d_2sm(sa + GEMM2_A_BYTES, &tmap_b, fb, kb * GEMM_BK, b_row);
+          if (p.mn_major & GEMM_A_MN) {        // operand stored [K, MN]: two 64 (MN) x 64 (k) boxes
+            tma_load_2d_2sm(sa, &tmap_a, fb, a_row, kb * GEMM_BK);
+            tma_load_2d_2sm(sa + GEMM_MN_LBO, &tmap_a, fb, a_row + 64, kb * GEMM_BK);
+          } else {
+            tma_load_2d_2sm(sa, &tmap_a, fb, kb * GEMM_BK, a_row);
+          }
+          if (p.mn_major & GEMM_B_MN) {
+            tma_load_2d_2sm(sa + GEMM2_A_BYTES, &tmap_b, fb, b_row, kb * GEMM_BK);
+            tma_load_2d_2sm(sa + GEMM2_A_BYTES + GEMM_MN_LBO, &tmap_b, fb, b_row + 64, kb * GEMM_BK);
+          } else {
+            tma_load_2d_2sm(sa + GEMM2_A_BYTES, &tmap_b, fb, kb * GEMM_BK, b_row);
+          }
         }
         __syncwarp();
         if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
@@ -154,8 +164,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   } else if (warp == WARP_MMA) {
     // ===== MMA issuer: the leader CTA's warp, one elected lane issues =====
     if (leader) {
-      constexpr uint32_t idesc = make_idesc_bf16(GEMM2_BM, GEMM_BN);
-      const uint64_t desc0 = make_smem_desc_sw128(smem_base);           // stage 0, A; +2/k-step, +stage bytes >> 4 per stage
+      const bool a_mn = p.mn_major & GEMM_A_MN, b_mn = p.mn_major & GEMM_B_MN;
+      const uint32_t idesc = make_idesc_bf16(GEMM2_BM, GEMM_BN) | (a_mn ? IDESC_A_MN_MAJOR : 0u) | (b_mn ? IDESC_B_MN_MAJOR : 0u);
+      // stage 0 descriptors; + k-step per UMMA_K (32 B along a K-major row, 2 KB = 16 lines of an MN-major tile), + stage bytes >> 4 per stage
+      const uint64_t adesc0 = a_mn ? make_smem_desc_mn_sw128(smem_base, GEMM_MN_LBO, GEMM_MN_SBO) : make_smem_desc_sw128(smem_base);
+      const uint64_t bdesc0 = b_mn ? make_smem_desc_mn_sw128(smem_base + GEMM2_A_BYTES, GEMM_MN_LBO, GEMM_MN_SBO)
+                                   : make_smem_desc_sw128(smem_base + GEMM2_A_BYTES);
+      const uint64_t ak = a_mn ? (GEMM_MN_KSTEP >> 4) : 2u, bk = b_mn ? (GEMM_MN_KSTEP >> 4) : 2u;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -168,12 +183,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * (GEMM2_STAGE_BYTES >> 4));
-            const uint64_t bdesc = adesc + static_cast<uint64_t>(GEMM2_A_BYTES >> 4);
+            const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (GEMM2_STAGE_BYTES >> 4));
+            const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (GEMM2_STAGE_BYTES >> 4));
             umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
-            umma_bf16_2sm(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);
-            umma_bf16_2sm(d_tmem, adesc + 4, bdesc + 4, idesc, 1u);
-            umma_bf16_2sm(d_tmem, adesc + 6, bdesc + 6, idesc, 1u);
+            umma_bf16_2sm(d_tmem, adesc + ak, bdesc + bk, idesc, 1u);
+            umma_bf16_2sm(d_tmem, adesc + 2 * ak, bdesc + 2 * bk, idesc, 1u);
+            umma_bf16_2sm(d_tmem, adesc + 3 * ak, bdesc + 3 * bk, idesc, 1u);
             umma_commit_2sm(empty_bar(stage));
             if (kb == k_blocks - 1) umma_commit_2sm(tfull_bar(acc));
           }

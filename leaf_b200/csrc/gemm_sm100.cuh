@@ -42,7 +42,15 @@ struct GemmParams {
   int ldc;
   int act;
   uint32_t tx_bytes;      // bytes one pipeline stage receives (TMA boxes are clamped to small tensors)
+  // mn_major: bit 0 = A is given MN-major ([K, M] row-major), bit 1 = B is given MN-major ([K, N] row-major) instead of the
+  // K-major [M, K] / [N, K]. The wgrad product dW[out,in] = dY[rows,out]^T . X[rows,in] reads dY and X as they lie (3), the
+  // dgrad product dX[rows,in] = dY[rows,out] . W[out,in] reads the forward's weight copy as it lies (2): no transposes.
+  int mn_major;
 };
+constexpr int GEMM_A_MN = 1, GEMM_B_MN = 2;
+// MN-major 128B-swizzled tile as TMA lays it down from a [K, MN] row-major tensor with a 64 (MN) x 64 (k) box: one 128-byte
+// line per k, 8-line groups 1 KB apart (SBO), the next 64 MN elements in the next box 8 KB on (LBO); 16 k = 2 KB.
+constexpr uint32_t GEMM_MN_LBO = 8192, GEMM_MN_SBO = 1024, GEMM_MN_KSTEP = 2048;
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -133,6 +141,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
 // kind::f16 instruction descriptor: D fp32, A/B bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+constexpr uint32_t IDESC_A_MN_MAJOR = 1u << 15, IDESC_B_MN_MAJOR = 1u << 16;
+// MN-major, 128-byte swizzled operand tile: 64 MN elements (128 B) contiguous, one 128-byte line per k, 8-line groups
+// `sbo` bytes apart, the next 64 MN elements `lbo` bytes away.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_sw128(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
 }
 
 __device__ __forceinline__ float fast_ex2(float x) {

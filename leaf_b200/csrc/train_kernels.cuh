@@ -1,7 +1,8 @@
 // K4: kernels of the backward pass of the selected adversarial batch (the FARE-style update,
 // /root/reference/utils_AT.py:312-337: encode_text(adv) in train mode, mse(...).sum(-1).mean(), backward).
-// All matrix products (dgrad and wgrad) run on the tcgen05 GEMM (gemm2_sm100.cuh) as K-major TN products; the kernels
-// here are the element-wise / per-row pieces around them and the operand transposes the wgrad products need.
+// All matrix products (dgrad and wgrad) run on the tcgen05 GEMM (gemm2_sm100.cuh), which reads weights and activations as
+// they lie (MN-major operands where the contraction runs over rows); the kernels here are the element-wise / per-row
+// pieces around them.
 // The batch is the B winners only (~3 % of the step's FLOPs), so these kernels are written for clarity and exact
 // fp32 math, not for the roofline.
 #pragma once
@@ -31,48 +32,33 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat1
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     g[i] = __float2bfloat16_rn(act_fwd_exact(__bfloat162float(u[i]), act));
 }
-// du = dg * act'(u)   (dg fp32 from the dgrad GEMM, du bf16 operand of the next GEMMs)
-__global__ void act_bwd_kernel(const float* __restrict__ dg, const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ du,
-                               size_t n, int act) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    du[i] = __float2bfloat16_rn(dg[i] * act_grad_exact(__bfloat162float(u[i]), act));
+// du = dg * act'(u)   (dg fp32 [R,C] from the dgrad GEMM, du bf16 operand of the next GEMMs); colsum != nullptr:
+// colsum[c] += sum_r du[r,c], the gradient of fc1's bias. A thread owns one column of a row band (coalesced across the CTA).
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dg, const __nv_bfloat16* __restrict__ u,
+                                                      __nv_bfloat16* __restrict__ du, int R, int C, int act, float* __restrict__ colsum) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  const int band = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * band, r1 = min(r0 + band, R);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) {
+    const size_t i = static_cast<size_t>(r) * C + c;
+    const __nv_bfloat16 v = __float2bfloat16_rn(dg[i] * act_grad_exact(__bfloat162float(u[i]), act));
+    du[i] = v;
+    s += __bfloat162float(v);
+  }
+  if (colsum && r1 > r0) atomicAdd(colsum + c, s);
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);
 }
 
-// ---- dst[C, Rp] (bf16) = src[R, C]^T, rows r >= R zero-filled (Rp = R rounded up to 8: TMA row pitch) --------------
-// colsum != nullptr: colsum[c] += sum_r src[r, c] as well (the bias gradient of the Linear whose wgrad operand this is):
-// the tile is in shared memory anyway, so the separate column-sum pass over the same matrix disappears.
 template <typename T>
 __device__ __forceinline__ float to_f32(T v);
 template <>
 __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
-
-template <typename T>
-__global__ void transpose_bf16_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int C, int Rp,
-                                      float* __restrict__ colsum = nullptr) {
-  __shared__ float tile[32][33];
-  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? to_f32<T>(src[static_cast<size_t>(r) * C + c]) : 0.f;
-  }
-  __syncthreads();
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int c = c0 + i, r = r0 + threadIdx.x;
-    if (c < C && r < Rp) dst[static_cast<size_t>(c) * Rp + r] = __float2bfloat16_rn(tile[threadIdx.x][i]);
-  }
-  if (colsum && threadIdx.y == 0 && c0 + threadIdx.x < C) {
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < 32; ++i) s += tile[i][threadIdx.x];
-    atomicAdd(colsum + c0 + threadIdx.x, s);
-  }
-}
 
 // ---- dst[C] += column sums of src[R, C] (bias gradients) -------------------------------------------------------------
 template <typename T>
@@ -100,14 +86,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                            const int* __restrict__ gather, int rows, int W,
                                                            const float* __restrict__ gamma, float eps, float* __restrict__ dx,
                                                            int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           __nv_bfloat16* __restrict__ dx16 = nullptr) {
+                                                           __nv_bfloat16* __restrict__ dx16 = nullptr,
+                                                           float* __restrict__ dxsum = nullptr) {
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  float4 dg_acc[VPL], db_acc[VPL], g[VPL];
+  // dxsum != nullptr: dxsum[c] += sum over rows of the dx written here - the bias gradient of the Linear whose output
+  // gradient this dx is (fc2 of the layer below for ln_1 / ln_final, out-proj for ln_2), so no separate column-sum pass
+  float4 dg_acc[VPL], db_acc[VPL], ds_acc[VPL], g[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     dg_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     db_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ds_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
   }
   const float invW = 1.f / static_cast<float>(W);
@@ -157,6 +147,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
       }
       out[lane + 32 * i] = o;
+      ds_acc[i].x += o.x; ds_acc[i].y += o.y; ds_acc[i].z += o.z; ds_acc[i].w += o.w;
       if (dx16) {                              // bf16 copy: the A operand of the next dgrad GEMM
         uint2 pk;
         pk.x = pack_bf16x2(o.x, o.y);
@@ -166,8 +157,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
   }
   // CTA-level reduction (warps take turns on a shared accumulator), then ONE atomic per column and CTA
-  __shared__ float red[2][VPL * 128];
-  for (int c = threadIdx.x; c < 2 * VPL * 128; c += blockDim.x) (&red[0][0])[c] = 0.f;
+  __shared__ float red[3][VPL * 128];
+  for (int c = threadIdx.x; c < 3 * VPL * 128; c += blockDim.x) (&red[0][0])[c] = 0.f;
   __syncthreads();
   for (int w = 0; w < (blockDim.x >> 5); ++w) {
     if ((threadIdx.x >> 5) == w) {
@@ -175,8 +166,10 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       for (int i = 0; i < VPL; ++i) {
         float* a = &red[0][(lane + 32 * i) * 4];
         float* b = &red[1][(lane + 32 * i) * 4];
+        float* d = &red[2][(lane + 32 * i) * 4];
         a[0] += dg_acc[i].x; a[1] += dg_acc[i].y; a[2] += dg_acc[i].z; a[3] += dg_acc[i].w;
         b[0] += db_acc[i].x; b[1] += db_acc[i].y; b[2] += db_acc[i].z; b[3] += db_acc[i].w;
+        d[0] += ds_acc[i].x; d[1] += ds_acc[i].y; d[2] += ds_acc[i].z; d[3] += ds_acc[i].w;
       }
     }
     __syncthreads();
@@ -184,6 +177,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int c = threadIdx.x; c < W; c += blockDim.x) {
     atomicAdd(dgamma + c, red[0][c]);
     atomicAdd(dbeta + c, red[1][c]);
+    if (dxsum) atomicAdd(dxsum + c, red[2][c]);
   }
 }
 

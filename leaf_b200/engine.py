@@ -366,6 +366,18 @@ class LeafEngine:
             check(self._lib.leaf_gemm_bf16(self._h, _ptr(A), _ptr(Bt), _ptr(bias), _ptr(C), M, N, K, epilogue, act, _ptr(m_dev), _stream()))
         return C
 
+    def gemm_mn(self, A, B, bias=None, epilogue=3, C=None, a_mn=True):
+        """B [K,N] MN-major; a_mn: A is [K,M] and C = A^T . B (the weight-gradient shape), else A is [M,K] and C = A . B
+        (the data-gradient shape)."""
+        K, N = B.shape
+        M = A.shape[1] if a_mn else A.shape[0]
+        if C is None:
+            C = torch.zeros((M, N), dtype=torch.bfloat16 if epilogue in (0, 1) else torch.float32, device=A.device)
+        with torch.cuda.device(self.device):
+            check(self._lib.leaf_gemm_bf16_mn(self._h, _ptr(A), _ptr(B), _ptr(bias), _ptr(C), M, N, K, epilogue, 1 if a_mn else 0,
+                                              _stream()))
+        return C
+
     def test_layernorm(self, x, gamma, beta):
         y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
         check(self._lib.leaf_test_layernorm(self._h, _ptr(x), x.shape[0], _ptr(gamma), _ptr(beta), _ptr(y), _stream()))

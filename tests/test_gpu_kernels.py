@@ -56,6 +56,27 @@ def test_gemm_epilogues(eng, M, N, K):
     assert torch.equal(R[m_live:], R0[m_live:])
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (256, 256, 4096), (1024, 4096, 4104), (3072, 1024, 6216), (64, 264, 40)])
+def test_gemm_mn_major_operands(eng, M, N, K):
+    """The K4 products read their operands as they lie: weight gradients C = A^T . B with A [K,M] and B [K,N] (both
+    MN-major), data gradients C = A . B with A [M,K] K-major and B [K,N] MN-major. K (the row count of a training batch)
+    is arbitrary for the weight-gradient shape: TMA zero-fills the ragged last block."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    At = (torch.randn((K, M), generator=g, device="cuda") * 0.5).to(torch.bfloat16)
+    B = (torch.randn((K, N), generator=g, device="cuda") * (K ** -0.5)).to(torch.bfloat16)
+    ref = At.float().T @ B.float()
+    C = eng.gemm_mn(At, B, None, epilogue=3)
+    assert torch.allclose(C, ref, atol=2e-3, rtol=1e-3), (C - ref).abs().max().item()
+    acc = torch.randn((M, N), generator=g, device="cuda")                     # += into an fp32 gradient buffer
+    acc0 = acc.clone()
+    eng.gemm_mn(At, B, None, epilogue=2, C=acc)
+    assert torch.allclose(acc, acc0 + ref, atol=2e-3, rtol=1e-3)
+    if K % 8 == 0:
+        C2 = eng.gemm_mn(At.T.contiguous(), B, None, epilogue=3, a_mn=False)
+        assert torch.allclose(C2, ref, atol=2e-3, rtol=1e-3), (C2 - ref).abs().max().item()
+        assert torch.equal(C2, C)                                              # same products, same order
+
+
 def test_gemm_duplicate_rows_bitwise_equal(eng):
     """Numerics must not depend on a row's position (hard part 5): duplicate candidates must tie."""
     g = torch.Generator(device="cuda").manual_seed(5)
