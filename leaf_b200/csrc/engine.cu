@@ -186,7 +186,7 @@ struct TimedSpan {
 // C[M,N] = A[M,K] . Bt[N,K]^T with the fused epilogue `epi`
 static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, const __nv_bfloat16* Bt, const float* bias,
                        void* C, int ldc, int M, int N, int K, int epi, int act, const int* m_dev, cudaStream_t st,
-                       const __nv_bfloat16* delta = nullptr, int mn_major = 0, long a_pitch = 0) {
+                       const __nv_bfloat16* delta = nullptr, int mn_major = 0, long a_pitch = 0, const float* res = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(LEAF_ERR_INVALID, "GEMM shape %dx%dx%d", M, N, K);
   if (N % 8 != 0) return fail(LEAF_ERR_INVALID, "GEMM N (%d) must be a multiple of 8", N);
   CUtensorMap ta, tb;
@@ -204,6 +204,7 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   } else if ((rc = make_tmap(e, Bt, N, K, b_box, &tb))) return rc;
   GemmParams p;
   p.mn_major = mn_major;
+  p.res = res;
   p.tx_bytes = static_cast<uint32_t>(a_box + b_box) * GEMM_BK * 2 * 2;       // both CTAs of the pair
   p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act; p.delta = delta;
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
@@ -771,7 +772,6 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
   t.N = N; t.M = M; t.T = mt[1];
   embed_kernel<<<N, 256, 0, st>>>(tok, t.meta, N, W, e->wp.token_embedding, e->wp.positional_embedding, t.L[0].x_in);
   e->launches++;
-  const size_t xbytes = static_cast<size_t>(M) * W * 4;
   for (int l = 0; l < e->cfg.layers; ++l) {
     const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
     const LayerW& w = e->lw[l];
@@ -780,15 +780,13 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
     if ((rc = launch_layernorm(e, a.x_in, nullptr, M, nullptr, p.ln1_w, p.ln1_b, a.h1, st))) return rc;
     if ((rc = launch_gemm(e, a.h1, t.rows_cap, w.qkv_w, w.qkv_b, a.qkv, 3 * W, M, 3 * W, W, EPI_BF16, 0, nullptr, st))) return rc;
     if ((rc = launch_attention(e, a.qkv, t.meta, N, a.o, 0, st))) return rc;
-    CK(cudaMemcpyAsync(a.x_mid, a.x_in, xbytes, cudaMemcpyDeviceToDevice, st));
-    if ((rc = launch_gemm(e, a.o, t.rows_cap, w.out_w, p.out_b, a.x_mid, W, M, W, W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    if ((rc = launch_gemm(e, a.o, t.rows_cap, w.out_w, p.out_b, a.x_mid, W, M, W, W, EPI_F32_RESIDUAL, 0, nullptr, st, nullptr, 0, 0, a.x_in))) return rc;
     if ((rc = launch_layernorm(e, a.x_mid, nullptr, M, nullptr, p.ln2_w, p.ln2_b, a.h2, st))) return rc;
     if ((rc = launch_gemm(e, a.h2, t.rows_cap, w.fc1_w, p.fc1_b, a.u, 4 * W, M, 4 * W, W, EPI_BF16, 0, nullptr, st))) return rc;
     const size_t nu = static_cast<size_t>(M) * 4 * W;
     act_fwd_kernel<<<launch_ew(e, nu), 256, 0, st>>>(a.u, a.g, nu, e->cfg.activation);
     e->launches++;
-    CK(cudaMemcpyAsync(x_next, a.x_mid, xbytes, cudaMemcpyDeviceToDevice, st));
-    if ((rc = launch_gemm(e, a.g, t.rows_cap, w.fc2_w, p.fc2_b, x_next, W, M, W, 4 * W, EPI_F32_RESIDUAL, 0, nullptr, st))) return rc;
+    if ((rc = launch_gemm(e, a.g, t.rows_cap, w.fc2_w, p.fc2_b, x_next, W, M, W, 4 * W, EPI_F32_RESIDUAL, 0, nullptr, st, nullptr, 0, 0, a.x_mid))) return rc;
   }
   if ((rc = launch_layernorm(e, t.x_out, nullptr, N, t.eos_row, e->wp.lnf_w, e->wp.lnf_b, t.pooled, st))) return rc;
   if ((rc = launch_gemm(e, t.pooled, t.max_seqs + 128, e->proj_w, nullptr, feat_out, E, N, E, W, EPI_F32, 0, nullptr, st))) return rc;

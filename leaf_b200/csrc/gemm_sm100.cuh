@@ -39,6 +39,8 @@ struct GemmParams {
   const float* bias;      // [N] or nullptr
   void* C;                // bf16 or fp32 [M, ldc]
   const __nv_bfloat16* delta;   // EPI_F32_RESIDUAL only, may be null: bf16 [M, ldc] added to the residual as well
+  const float* res;             // EPI_F32_RESIDUAL only, may be null: the residual is read from res [M, ldc] instead of C
+                                // (C = res + acc + bias: the training forward keeps the block input, so no copy first)
   int ldc;
   int act;
   uint32_t tx_bytes;      // bytes one pipeline stage receives (TMA boxes are clamped to small tensors)
@@ -207,7 +209,7 @@ __device__ __forceinline__ void epilogue_load_residual(const GemmParams& p, Resi
       const int row = row0 + it * 8 + (lane >> 2);
       const int col = col0 + h * 16 + c * 4;
       if (row < M && col < p.N)
-        r.x[h * 4 + it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.C) + static_cast<size_t>(row) * p.ldc + col);
+        r.x[h * 4 + it] = *reinterpret_cast<const float4*>((p.res ? p.res : reinterpret_cast<const float*>(p.C)) + static_cast<size_t>(row) * p.ldc + col);
     }
   }
 }
