@@ -40,7 +40,23 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
   if (c >= C) return;
   const int band = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * band, r1 = min(r0 + band, R);
   float s = 0.f;
-  for (int r = r0; r < r1; ++r) {
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {                 // four independent rows in flight per thread
+    float d[4], uu[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t i = static_cast<size_t>(r + k) * C + c;
+      d[k] = dg[i];
+      uu[k] = __bfloat162float(u[i]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const __nv_bfloat16 v = __float2bfloat16_rn(d[k] * act_grad_exact(uu[k], act));
+      du[static_cast<size_t>(r + k) * C + c] = v;
+      s += __bfloat162float(v);
+    }
+  }
+  for (; r < r1; ++r) {
     const size_t i = static_cast<size_t>(r) * C + c;
     const __nv_bfloat16 v = __float2bfloat16_rn(dg[i] * act_grad_exact(__bfloat162float(u[i]), act));
     du[i] = v;
