@@ -214,9 +214,11 @@ int leaf_set_prune_last(leaf_handle_t h, int32_t on);
 int64_t leaf_launch_count(leaf_handle_t h, int32_t reset);
 /* Packed-row count (sum of len) of the last leaf_encode; synchronises the device. */
 int64_t leaf_last_rows(leaf_handle_t h);
-/* Accumulated device time (ms) of the launches of class `which` (0 = GEMM, 1 = LayerNorm, 2 = attention, 3 = row
- * packing + embedding, 4 + e = the GEMM launches with epilogue e, 8 = the residual GEMMs with K > N, i.e. fc2) between CUDA events recorded on the launching stream, since timing was last enabled with
- * leaf_set_timing(h, 1). Synchronises on the recorded events. */
+/* Accumulated device time (ms) of the launches of class `which` between CUDA events recorded on the launching stream, since
+ * timing was last enabled with leaf_set_timing(h, 1): 0 = every GEMM, 1 = LayerNorm, 2 = attention, 3 = row packing +
+ * embedding, 4 + e = the GEMM launches with epilogue e (0 bf16 store with N != K: QKV; 1 activation: fc1; 2 residual; 3 fp32
+ * store: projection), 8 = the residual GEMMs with K > N (fc2; counted in class 6 as well), 9 = bf16 store with N == K
+ * (out-proj). Synchronises on the recorded events. */
 int leaf_set_timing(leaf_handle_t h, int32_t on);
 double leaf_timing_ms(leaf_handle_t h, int32_t which, int32_t* launches);
 
