@@ -196,12 +196,12 @@ def run_ours(a):
     def device_step(pos_d, chr_d, record=None):
         """The hot path with inputs resident in HBM (k = 1 form: no host round trip between the phases)."""
         tok, ln, base = eng.expand_tokenize(caps_d, off_d, B, n, pos=pos_d, chr_=space)
-        f = eng.encode_tokens(tok, ln, False, base, (B * n, n))
+        f = eng.encode_tokens(tok, ln, False, base, (B * n, n), trim=True)
         if record is not None:
             record.append((ln[:B * n], eng.last_rows()))
         best1, _, _ = eng.score(f, anchor, B, n, "l2")
         tok, ln, base = eng.expand_tokenize(caps_d, off_d, B, n, pos=pos_d, chr_=chr_d, sel=best1)
-        f = eng.encode_tokens(tok, ln, False, base, (B * n, n))
+        f = eng.encode_tokens(tok, ln, False, base, (B * n, n), trim=True)
         if record is not None:
             record.append((ln[:B * n], eng.last_rows()))
         return eng.score(f, anchor, B, n, "l2")

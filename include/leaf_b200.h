@@ -144,9 +144,13 @@ int leaf_constrain_mask(leaf_handle_t h, const uint8_t* caps, const int32_t* cap
  * bit-identical to base == NULL.
  * dedup_group > 1: rows [0, dedup_rows) come in groups of dedup_group consecutive rows (the n candidates of a sample);
  * a row whose tokens equal an EARLIER row of its group is not encoded again - it receives that row's features (bit
- * identical, so exact ties keep resolving to the first index). dedup_group <= 1 disables it. */
+ * identical, so exact ties keep resolving to the first index). dedup_group <= 1 disables it.
+ * trim_providers != 0 (with base and 0 < dedup_rows < N): the caller does not read feat_out of the rows [dedup_rows, N) that
+ * other rows name as base (the unedited captions of an attack phase: utils_attacks.py never encodes them at all, here they
+ * exist so that their prefixes are computed once). They are computed only as far as some row reads them and their feat_out
+ * rows are UNDEFINED; every other row is unchanged, bit for bit. */
 int leaf_encode(leaf_handle_t h, const int32_t* tok, const int32_t* len, const int32_t* base, int32_t N,
-                int32_t dedup_rows, int32_t dedup_group, int32_t normalize, float* feat_out, void* stream);
+                int32_t dedup_rows, int32_t dedup_group, int32_t trim_providers, int32_t normalize, float* feat_out, void* stream);
 
 /* ---- K3: TextFARE score + per-sample argmax ----------------------------------------------------
  * Replaces utils_attacks.py:332-348 / :370-386 / :393. feat [B*n,E] fp32, anchor [B,E] fp32.

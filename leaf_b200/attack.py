@@ -178,7 +178,7 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
                 SS = [[generate_sentence(S, int(z), 32) for z in pos_l[i]] for i, S in enumerate(mine)]
                 valid1 = _valid_mask(valid_fn, mine, SS, Bl, nl, dev)
             tok, ln, base = eng.expand_tokenize(caps_d, off_d, Bl, nl, pos=pos_d, chr_=chr1_d, valid=valid1)
-            feats = eng.encode_tokens(tok, ln, normalize, base, (Bl * nl, nl))   # rows [0, Bl*nl): candidates, then Bl captions
+            feats = eng.encode_tokens(tok, ln, normalize, base, (Bl * nl, nl), trim=True)   # rows [0, Bl*nl): candidates, then Bl captions
             best1, _, loss1 = eng.score(feats, anchor, Bl, nl, objective, want_loss=(debug or shard == "candidates"))
         us = np.stack([_DRAW(len(V), n) for _ in sentences])                                                     # :236
         chars2 = Vt[us]
@@ -201,7 +201,7 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
                 SS = [[generate_sentence(S, int(zs_l[i]), int(c)) for c in chr2_l[i]] for i, S in enumerate(mine)]
                 valid2 = _valid_mask(valid_fn, mine, SS, Bl, nl, dev)
             tok, ln, base = eng.expand_tokenize(caps_d, off_d, Bl, nl, pos=pos2_d, chr_=chr2_d, sel=sel, valid=valid2)
-            feats = eng.encode_tokens(tok, ln, normalize, base, (Bl * nl, nl))
+            feats = eng.encode_tokens(tok, ln, normalize, base, (Bl * nl, nl), trim=True)
             best2, feat_l, loss2 = eng.score(feats, anchor, Bl, nl, objective, want_loss=(debug or shard == "candidates"))
             g2 = best2.long()
             okv = torch.ones(Bl, dtype=torch.bool, device=dev) if valid2 is None else \

@@ -105,7 +105,7 @@ struct leaf_engine {
   float* xc = nullptr;                // [max_seqs, W] fp32 residual rows of the pooled positions (final layer, compact)
   int* first_of = nullptr;            // [max_seqs] sequence whose rows stand for sequence i
   bool prune_last = true;             // final layer: out-proj + MLP on the pooled rows only
-  int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr, *dup_of = nullptr;
+  int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr, *dup_of = nullptr, *need = nullptr;
   int4* meta = nullptr;
   // bookkeeping
   int64_t launches = 0;
@@ -272,9 +272,9 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
 static void free_workspace(leaf_engine* e) {
   cudaFree(e->x); cudaFree(e->h); cudaFree(e->big); cudaFree(e->pooled); cudaFree(e->xc); cudaFree(e->first_of); cudaFree(e->dlt);
   e->xc = nullptr; e->first_of = nullptr; e->dlt = nullptr;
-  cudaFree(e->cu); cudaFree(e->eos_row); cudaFree(e->total_rows); cudaFree(e->pfx); cudaFree(e->own_len); cudaFree(e->dup_of); cudaFree(e->meta);
+  cudaFree(e->cu); cudaFree(e->eos_row); cudaFree(e->total_rows); cudaFree(e->pfx); cudaFree(e->own_len); cudaFree(e->dup_of); cudaFree(e->need); cudaFree(e->meta);
   e->x = nullptr; e->h = nullptr; e->big = nullptr; e->pooled = nullptr;
-  e->cu = e->eos_row = e->total_rows = e->pfx = e->own_len = e->dup_of = nullptr;
+  e->cu = e->eos_row = e->total_rows = e->pfx = e->own_len = e->dup_of = e->need = nullptr;
   e->meta = nullptr;
   e->max_seqs = 0; e->rows_cap = 0;
   e->tmaps.clear();
@@ -435,6 +435,7 @@ extern "C" int leaf_reserve(leaf_handle_t e, int32_t max_seqs) {
   CK(cudaMalloc(&e->pfx, static_cast<size_t>(max_seqs) * 4));
   CK(cudaMalloc(&e->own_len, static_cast<size_t>(max_seqs) * 4));
   CK(cudaMalloc(&e->dup_of, static_cast<size_t>(max_seqs) * 4));
+  CK(cudaMalloc(&e->need, static_cast<size_t>(max_seqs) * 4));
   CK(cudaMalloc(&e->meta, static_cast<size_t>(max_seqs) * 16));
   CK(cudaMalloc(&e->total_rows, 4));
   CK(cudaMemset(e->total_rows, 0, 4));
@@ -494,7 +495,8 @@ static int launch_attention(leaf_engine* e, const __nv_bfloat16* qkv, const int4
 }
 
 extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* len, const int32_t* base, int32_t N,
-                           int32_t dedup_rows, int32_t dedup_group, int32_t normalize, float* feat_out, void* stream) {
+                           int32_t dedup_rows, int32_t dedup_group, int32_t trim_providers, int32_t normalize, float* feat_out,
+                           void* stream) {
   if (!e || !tok || !len || !feat_out) return fail(LEAF_ERR_INVALID, "null argument");
   if (!e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
   if (N <= 0) return fail(LEAF_ERR_INVALID, "N=%d", N);
@@ -512,7 +514,13 @@ extern "C" int leaf_encode(leaf_handle_t e, const int32_t* tok, const int32_t* l
     e->launches++;
     dup = e->dup_of;
   }
-  prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, base, dup, N, e->pfx, e->own_len);
+  const bool trim = trim_providers && base && dedup_rows > 0 && dedup_rows < N;
+  if (trim) CK(cudaMemsetAsync(e->need, 0, static_cast<size_t>(N) * 4, st));
+  prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, base, dup, N, e->pfx, e->own_len, trim ? e->need : nullptr);
+  if (trim) {
+    trim_providers_kernel<<<(N - dedup_rows + 255) / 256, 256, 0, st>>>(base, e->need, dedup_rows, N, e->own_len);
+    e->launches++;
+  }
   scan_lengths_kernel<<<1, 1024, 0, st>>>(e->own_len, N, e->cu, e->total_rows);
   meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(e->cu, e->pfx, base, dup, N, e->meta, e->eos_row, e->first_of);
   embed_kernel<<<N, 256, 0, st>>>(tok, e->meta, N, W, e->wp.token_embedding, e->wp.positional_embedding, e->x);

@@ -73,9 +73,11 @@ __global__ void __launch_bounds__(1024) scan_lengths_kernel(const int* __restric
 // own_len[i] = t - p with p = min(common prefix, t - 1) (the pooled EOS row is always computed). One warp per row.
 // ---------------------------------------------------------------------------------------------
 // dup_of[i] >= 0 (from dedup_kernel): row i has the same tokens as an earlier row and owns NO rows at all.
+// need != nullptr: need[b] = max over the rows that name b as their base of the prefix length they read from it (zeroed by
+// the caller); trim_providers_kernel then cuts the base rows down to that many positions.
 __global__ void __launch_bounds__(256) prefix_kernel(const int* __restrict__ tok, const int* __restrict__ len,
                                                      const int* __restrict__ base, const int* __restrict__ dup_of, int N,
-                                                     int* __restrict__ pfx, int* __restrict__ own_len) {
+                                                     int* __restrict__ pfx, int* __restrict__ own_len, int* __restrict__ need = nullptr) {
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= N) return;
   const int t = min(max(len[i], 1), 77);
@@ -96,8 +98,20 @@ __global__ void __launch_bounds__(256) prefix_kernel(const int* __restrict__ tok
       if (m) { p = c + __ffs(m) - 1; break; }
     }
     p = min(p, t - 1);
+    if (need && lane == 0 && p > 0) atomicMax(need + b, p);
   }
   if (lane == 0) { pfx[i] = p; own_len[i] = t - p; }
+}
+
+// Rows [first, N) with base == -1 are PROVIDERS when the caller does not read their features (the unedited captions of an
+// attack phase, which exist only so that the candidates can share their prefix): only the positions some candidate
+// actually reads are kept (at least one, so that the row still has a pooled position). With the TextFARE objective the
+// winning edit position of phase 1 sits in the first words, so in phase 2 a caption shrinks from ~32 rows to ~3.
+__global__ void trim_providers_kernel(const int* __restrict__ base, const int* __restrict__ need, int first, int N,
+                                      int* __restrict__ own_len) {
+  const int i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N || (base && base[i] >= 0)) return;
+  own_len[i] = max(1, min(own_len[i], need[i]));
 }
 
 // Duplicate candidates inside a sample (e.g. 'a' and 'A' written at the same position: the tokenizer lower-cases, so

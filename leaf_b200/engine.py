@@ -290,11 +290,12 @@ class LeafEngine:
 
     # ---- K2 ----------------------------------------------------------------------------------------------
     def encode_tokens(self, tok: torch.Tensor, lengths: torch.Tensor = None, normalize: bool = False,
-                      base: torch.Tensor = None, dedup=(0, 0)) -> torch.Tensor:
+                      base: torch.Tensor = None, dedup=(0, 0), trim: bool = False) -> torch.Tensor:
         """CLIP.encode_text (model.py:269-284) for token rows already on the device. `base` (int32 [N], -1 = none)
         names for each row another row of the batch it shares a token prefix with (computed once, results identical).
         dedup = (rows, group): the first `rows` rows come in groups of `group` candidates of one sample; duplicates
-        inside a group are encoded once."""
+        inside a group are encoded once. trim=True: the rows after them that serve as `base` (the unedited captions) are
+        computed only as far as a candidate reads them; THEIR rows of the result are undefined, all others unchanged."""
         if tok.dtype != torch.int32:
             tok = tok.to(torch.int32)
         tok = tok.contiguous()
@@ -304,7 +305,7 @@ class LeafEngine:
         self.reserve(N)
         out = torch.empty((N, self.embed_dim), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(self._lib.leaf_encode(self._h, _ptr(tok), _ptr(lengths.contiguous()), _ptr(base), N, int(dedup[0]), int(dedup[1]),
+            check(self._lib.leaf_encode(self._h, _ptr(tok), _ptr(lengths.contiguous()), _ptr(base), N, int(dedup[0]), int(dedup[1]), 1 if trim else 0,
                                         1 if normalize else 0, _ptr(out), _stream()))
         return out
 

@@ -49,7 +49,7 @@ def _score_list(eng, eng2, sentence, pos, chr_, anchor, anchor2, objective, vali
             out.append(None)
             continue
         e.reserve(groups * per + groups)
-        feats = e.encode_tokens(tok, ln, norm, base, (groups * per, per))
+        feats = e.encode_tokens(tok, ln, norm, base, (groups * per, per), trim=True)
         _, _, loss = e.score(feats, a.expand(groups, -1).contiguous(), groups, per, objective, want_loss=True)
         out.append(loss)
     return out + [valid_d]

@@ -46,7 +46,7 @@ class OracleEngine:
             base = -np.ones(B, dtype=np.int32)
         return torch.from_numpy(tok), torch.from_numpy(ln), torch.from_numpy(base)
 
-    def encode_tokens(self, tok, ln=None, normalize=False, base=None, dedup=(0, 0)):
+    def encode_tokens(self, tok, ln=None, normalize=False, base=None, dedup=(0, 0), trim=False):
         self.encoded_rows += tok.shape[0]
         with torch.no_grad():
             return O.encode_text(self.sd, tok.long(), self.heads, quick_gelu=self.quick, normalize=normalize)

@@ -137,6 +137,15 @@ def test_shared_prefix_is_bit_identical():
     ref = eng.encode_tokens(tok, ln, False, None)
     assert torch.equal(ded, ref)
     assert rows_ded < 0.8 * eng.encode_tokens(tok, ln, False, base).shape[0] * 77 and rows_ded < rows_shared
+    # provider trimming: the caption rows are cut down to the prefix some candidate reads; every candidate row keeps its bits
+    trimmed = eng.encode_tokens(tok, ln, False, base, (B * n, n), trim=True)
+    assert torch.equal(trimmed[:B * n], ded[:B * n]) and eng.last_rows() < rows_ded
+    same_pos = np.repeat(pos[:, :1], n, axis=1)                               # phase-2 shape: one position per sample
+    tok2, ln2, base2 = eng.expand_tokenize(d, o, B, n, torch.from_numpy(same_pos).cuda(), torch.from_numpy(chr_).cuda())
+    full2 = eng.encode_tokens(tok2, ln2, False, base2, (B * n, n))
+    rows_full2 = eng.last_rows()
+    trim2 = eng.encode_tokens(tok2, ln2, False, base2, (B * n, n), trim=True)
+    assert torch.equal(trim2[:B * n], full2[:B * n]) and eng.last_rows() < rows_full2
     # final-layer pruning (out-proj / MLP on the pooled EOS rows only) changes no bit either
     eng.set_prune_last(False)
     try:

@@ -33,11 +33,11 @@ flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 rows = []
 def step(pos, ch, rec=False):
     tok, ln, base = eng.expand_tokenize(d, o, B, n, pos=pos, chr_=space)
-    f = eng.encode_tokens(tok, ln, False, base, (B * n, n))
+    f = eng.encode_tokens(tok, ln, False, base, (B * n, n), trim=True)
     if rec: rows.append(eng.last_rows())
     best = eng.score(f, anchor, B, n, "l2")[0]
     tok, ln, base = eng.expand_tokenize(d, o, B, n, pos=pos, chr_=ch, sel=best)
-    f = eng.encode_tokens(tok, ln, False, base, (B * n, n))
+    f = eng.encode_tokens(tok, ln, False, base, (B * n, n), trim=True)
     if rec: rows.append(eng.last_rows())
     return eng.score(f, anchor, B, n, "l2")
 D = [draws(s) for s in range(8)]

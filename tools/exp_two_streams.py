@@ -47,12 +47,12 @@ def step(parts):
     for i, p in enumerate(parts):                            # phase 1 of every part, then phase 2: launches are asynchronous
         with torch.cuda.stream(p["stream"]):
             tok, ln, base = p["eng"].expand_tokenize(p["d"], p["o"], p["b"], n, pos=p["pos"], chr_=p["space"])
-            f = p["eng"].encode_tokens(tok, ln, False, base, (p["b"] * n, n))
+            f = p["eng"].encode_tokens(tok, ln, False, base, (p["b"] * n, n), trim=True)
             best[i] = p["eng"].score(f, p["anchor"], p["b"], n, "l2")[0]
     for i, p in enumerate(parts):
         with torch.cuda.stream(p["stream"]):
             tok, ln, base = p["eng"].expand_tokenize(p["d"], p["o"], p["b"], n, pos=p["pos"], chr_=p["ch"], sel=best[i])
-            f = p["eng"].encode_tokens(tok, ln, False, base, (p["b"] * n, n))
+            f = p["eng"].encode_tokens(tok, ln, False, base, (p["b"] * n, n), trim=True)
             p["eng"].score(f, p["anchor"], p["b"], n, "l2")
 
 

@@ -29,10 +29,10 @@ d, o = eng.upload_captions(caps)
 
 def step():
     tok, ln, base = eng.expand_tokenize(d, o, B, n, pos=pos, chr_=space)
-    f = eng.encode_tokens(tok, ln, False, base, (B * n, n))
+    f = eng.encode_tokens(tok, ln, False, base, (B * n, n), trim=True)
     best1, _, _ = eng.score(f, anchor, B, n, "l2")
     tok, ln, base = eng.expand_tokenize(d, o, B, n, pos=pos, chr_=ch, sel=best1)
-    f = eng.encode_tokens(tok, ln, False, base, (B * n, n))
+    f = eng.encode_tokens(tok, ln, False, base, (B * n, n), trim=True)
     return eng.score(f, anchor, B, n, "l2")
 
 
