@@ -803,17 +803,6 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
   return LEAF_OK;
 }
 
-template <typename Tp>
-static int launch_colsum(leaf_engine* e, const Tp* src, int R, int C, int ld, float* dst, cudaStream_t st) {
-  if (!dst) return LEAF_OK;
-  int gy = (R + 255) / 256;
-  if (gy > 64) gy = 64;
-  colsum_kernel<Tp><<<dim3((C + 31) / 32, gy), 256, 0, st>>>(src, R, C, ld, dst);
-  e->launches++;
-  CK(cudaGetLastError());
-  return LEAF_OK;
-}
-
 static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x, const int* gather, int rows, const float* gamma,
                                 float* dx, int accumulate, float* dgamma, float* dbeta, float* scratch, cudaStream_t st,
                                 __nv_bfloat16* dx16 = nullptr, float* dxsum = nullptr) {
@@ -897,20 +886,21 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
     // ================= attention branch: x_mid = x_in + out_proj(attn(in_proj(ln_1(x_in)))) =================
     if ((rc = dgrad(t.dx16, cap, w.out_w, t.dtmp, M, W, W))) return rc;                                     // do [M,W]
     if (g.out_w && (rc = wgrad(t.dx16, 0, a.o, F(g.out_w), M, W, W))) return rc;
-    attention_bwd_kernel<<<dim3(N, e->cfg.heads), 32, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16);   // dqkv [M,3W] bf16
+    {                                                                                                        // dqkv [M,3W] bf16 (+ in-projection bias grads)
+      float* bq = p.in_proj_w ? F(g.in_proj_b) : F(g.q_b);
+      float* bk = p.in_proj_w ? (g.in_proj_b ? F(g.in_proj_b) + W : nullptr) : F(g.k_b);
+      float* bv = p.in_proj_w ? (g.in_proj_b ? F(g.in_proj_b) + 2 * W : nullptr) : F(g.v_b);
+      attention_bwd_kernel<<<dim3(N, e->cfg.heads), 32, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16, bq, bk, bv);
+    }
     e->launches++;
     CK(cudaGetLastError());
     if ((rc = dgrad(t.d16, cap, w.qkv_w, t.dtmp, M, W, 3 * W))) return rc;                                  // dh1 [M,W]
     if (p.in_proj_w) {                                                                                       // layout of the bound parameters
       if (g.in_proj_w && (rc = wgrad(t.d16, 0, a.h1, F(g.in_proj_w), M, W, 3 * W))) return rc;
-      if ((rc = launch_colsum(e, t.d16, M, 3 * W, 3 * W, F(g.in_proj_b), st))) return rc;
     } else {                                                                                                 // HF: q, k, v are column blocks of dqkv
       const float* dw[3] = {g.q_w, g.k_w, g.v_w};
-      const float* db[3] = {g.q_b, g.k_b, g.v_b};
-      for (int j = 0; j < 3; ++j) {
+      for (int j = 0; j < 3; ++j)
         if (dw[j] && (rc = wgrad(t.d16 + j * W, 3 * W, a.h1, F(dw[j]), M, W, W))) return rc;
-        if ((rc = launch_colsum(e, t.d16 + j * W, M, W, 3 * W, F(db[j]), st))) return rc;
-      }
     }
     if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_in, nullptr, M, p.ln1_w, t.dx, 1, F(g.ln1_w), F(g.ln1_b), scratch, st, t.dx16,
                                    l > 0 ? F(grads->layers[l - 1].fc2_b) : nullptr))) return rc;

@@ -76,24 +76,6 @@ __device__ __forceinline__ float to_f32<float>(float v) { return v; }
 template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
-// ---- dst[C] += column sums of src[R, C] (bias gradients) -------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ src, int R, int C, int ld, float* __restrict__ dst) {
-  __shared__ float part[8][32];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
-  float s = 0.f;
-  if (c < C)
-    for (int r = blockIdx.y * 8 + w; r < R; r += gridDim.y * 8) s += to_f32<T>(src[static_cast<size_t>(r) * ld + c]);
-  part[w][threadIdx.x & 31] = s;
-  __syncthreads();
-  if (w == 0 && c < C) {
-    float t = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) t += part[i][threadIdx.x];
-    atomicAdd(dst + c, t);
-  }
-}
-
 // ---- LayerNorm backward: dx[row] (+)= rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += dy*xhat; dbeta += dy
 // One warp per row. gather != nullptr: row r reads x[gather[r]] and WRITES dx[gather[r]] (final LN on the pooled rows).
 // accumulate: dx += (residual branch) instead of dx = .
@@ -322,9 +304,29 @@ __device__ __forceinline__ void attb_query_tile(uint32_t sQ, uint32_t sK, uint32
   }
 }
 
+// Column sums of a 16 x 64 accumulator tile (8 n8 blocks) over its 16 rows, left on the lanes with g == 0 (lane c holds
+// columns 8 n8 + 2c, +1): the bias gradient of the in-projection is the column sum of dQ | dK | dV.
+__device__ __forceinline__ void attb_colsum(const float (&acc)[8][4], float (&sum)[8][2]) {
+#pragma unroll
+  for (int n8 = 0; n8 < 8; ++n8) {
+    float a = acc[n8][0] + acc[n8][2], b = acc[n8][1] + acc[n8][3];
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    sum[n8][0] += a;
+    sum[n8][1] += b;
+  }
+}
+
+// db_q / db_k / db_v (each may be null): [W] fp32, += the column sums of dQ / dK / dV (the in-projection's bias gradient;
+// the rows beyond a sequence's length are exactly zero in all three, so they do not disturb the sums)
 __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
                                                            const float* __restrict__ dout, const int4* __restrict__ meta,
-                                                           int W, int T, __nv_bfloat16* __restrict__ dqkv) {
+                                                           int W, int T, __nv_bfloat16* __restrict__ dqkv,
+                                                           float* __restrict__ db_q = nullptr, float* __restrict__ db_k = nullptr,
+                                                           float* __restrict__ db_v = nullptr) {
   extern __shared__ __align__(16) uint8_t attb_sm[];
   const int T16 = (T + 15) / 16 * 16, PP = T16 + 8;
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attb_sm);
@@ -370,6 +372,9 @@ __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* 
   const uint32_t sQ = smem_u32(Qs), sK = smem_u32(Ks), sV = smem_u32(Vs), sdO = smem_u32(dOs);
   const int g = lane >> 2, c = lane & 3;
   // ---- pass 1: per query tile S, dP, softmax, dS, dQ; P and dS to shared memory ----
+  float sq[8][2], sk[8][2], sv[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sq[i][0] = sq[i][1] = sk[i][0] = sk[i][1] = sv[i][0] = sv[i][1] = 0.f;
   for (int qi = 0; qi < nt16; ++qi) {
     float dq[8][4];
     switch (qi) {                                          // warp-uniform
@@ -380,6 +385,7 @@ __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* 
       default: attb_query_tile<5>(sQ, sK, sV, sdO, Ps, dSs, Dv, PP, lane, dq); break;
     }
     const int i0 = 16 * qi + g, i1 = i0 + 8;
+    if (db_q) attb_colsum(dq, sq);
 #pragma unroll
     for (int n8 = 0; n8 < 8; ++n8) {
       __nv_bfloat16* dst = dqkv + head * 64 + 8 * n8 + 2 * c;
@@ -415,6 +421,8 @@ __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* 
       }
     }
     const int j0 = 16 * kj + g, j1 = j0 + 8;
+    if (db_k) attb_colsum(dk, sk);
+    if (db_v) attb_colsum(dv, sv);
 #pragma unroll
     for (int n8 = 0; n8 < 8; ++n8) {
       __nv_bfloat16* dst = dqkv + head * 64 + 8 * n8 + 2 * c;
@@ -426,6 +434,15 @@ __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* 
         *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + j1) * ld + W) = pack_bf16x2(dk[n8][2], dk[n8][3]);
         *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + j1) * ld + 2 * W) = pack_bf16x2(dv[n8][2], dv[n8][3]);
       }
+    }
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int n8 = 0; n8 < 8; ++n8) {
+      const int col = head * 64 + 8 * n8 + 2 * c;
+      if (db_q) { atomicAdd(db_q + col, sq[n8][0]); atomicAdd(db_q + col + 1, sq[n8][1]); }
+      if (db_k) { atomicAdd(db_k + col, sk[n8][0]); atomicAdd(db_k + col + 1, sk[n8][1]); }
+      if (db_v) { atomicAdd(db_v + col, sv[n8][0]); atomicAdd(db_v + col + 1, sv[n8][1]); }
     }
   }
 }
