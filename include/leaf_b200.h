@@ -174,10 +174,17 @@ int leaf_topk(leaf_handle_t h, const float* score_a, const float* score_b, int32
  * leaf_forward_train computes feat_out [N,E] fp32 and keeps every layer's activations (it synchronises the stream once
  * to learn the packed row count); leaf_backward consumes dfeat [N,E] fp32 and ACCUMULATES (+=) the parameter
  * gradients into the fp32 device buffers named by `grads` (same struct and layouts as leaf_bind_weights; a NULL
- * pointer marks a frozen parameter). bf16 operands, fp32 accumulation, fp32 LayerNorm/softmax/activation math. */
+ * pointer marks a frozen parameter). bf16 operands, fp32 accumulation, fp32 LayerNorm/softmax/activation math.
+ * ONE forward, ONE backward: the engine keeps a single activation store. Every leaf_forward_train gets a generation
+ * number (> 0, written to *generation_out when that is not NULL); leaf_backward(generation != 0) fails with
+ * LEAF_ERR_STATE when the store holds a different forward (a second encode_text ran before this output's backward -
+ * torch autograd would differentiate each output through its own graph, utils_AT.py:317-337 has exactly one), and with
+ * LEAF_ERR_INVALID when dfeat_rows is not the N of that forward. The store is consumed by a successful backward. */
 int leaf_train_reserve(leaf_handle_t h, int32_t max_seqs);
-int leaf_forward_train(leaf_handle_t h, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out, void* stream);
-int leaf_backward(leaf_handle_t h, const float* dfeat, const leaf_weight_ptrs_t* grads, void* stream);
+int leaf_forward_train(leaf_handle_t h, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out,
+                       int64_t* generation_out, void* stream);
+int leaf_backward(leaf_handle_t h, int64_t generation, const float* dfeat, int32_t dfeat_rows, const leaf_weight_ptrs_t* grads,
+                  void* stream);
 
 /* AdamW (torch.optim.AdamW semantics, decoupled weight decay) over the tower's parameters held in ONE flat fp32 buffer
  * (train_AT_text_only.py:326-341: the gain / bias / LayerNorm group with weight_decay 0 is laid out first, elements

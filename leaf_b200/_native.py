@@ -46,8 +46,8 @@ SIGNATURES = {
     "leaf_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "leaf_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "leaf_train_reserve": (c_int, [c_void_p, c_int]),
-    "leaf_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p]),
-    "leaf_backward": (c_int, [c_void_p, c_void_p, ctypes.POINTER(LeafWeightPtrs), c_void_p]),
+    "leaf_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, ctypes.POINTER(c_i64), c_void_p]),
+    "leaf_backward": (c_int, [c_void_p, c_i64, c_void_p, c_int, ctypes.POINTER(LeafWeightPtrs), c_void_p]),
     "leaf_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_float, ctypes.c_float,
                            ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int, ctypes.c_float, c_void_p]),
     "leaf_sumsq": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),

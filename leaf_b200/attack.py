@@ -23,7 +23,7 @@ import torch
 
 from . import dist as D
 from ._native import LeafError
-from .engine import LeafEngine, OBJECTIVES
+from .engine import LeafEngine, OBJECTIVES, bind_module
 
 # /root/reference/train_AT_text_only.py:93
 V_DEFAULT = [-1] + [ord(c) for c in string.ascii_lowercase + " " + string.ascii_uppercase
@@ -50,35 +50,17 @@ def _to_dev(a: np.ndarray, dev) -> torch.Tensor:
 
 
 def _engine_of(model) -> LeafEngine:
+    """The engine behind `model`: a LeafTextTower / LeafEngine (or an engine double with the same three methods), or any
+    torch module in open_clip CLIP / HF CLIPTextModel(WithProjection) / HF CLIPModel naming, also behind a DDP-style
+    `.module` holder (engine.bind_module: created on first use, cached on the module, re-cast when its parameters have
+    changed in place since the last call)."""
     if isinstance(model, LeafEngine) or all(hasattr(model, a) for a in ("expand_tokenize", "encode_tokens", "score")):
         return model
     eng = getattr(model, "leaf_engine", None)
-    if isinstance(eng, LeafEngine):
+    if isinstance(eng, LeafEngine) and not isinstance(model, torch.nn.Module):
         return eng
-    if isinstance(model, torch.nn.Module):                        # bind a foreign tower (open_clip CLIP / HF) once
-        module = model.module if hasattr(model, "module") and isinstance(model.module, torch.nn.Module) else model
-        params = {k: v.detach() for k, v in module.state_dict(keep_vars=True).items()}
-        heads = None
-        for path in ("transformer.resblocks.0.attn.num_heads", "text.transformer.resblocks.0.attn.num_heads",
-                     "config.num_attention_heads", "text_model.config.num_attention_heads"):
-            obj = module
-            try:
-                for part in path.split("."):
-                    obj = obj[int(part)] if part.isdigit() else getattr(obj, part)
-                heads = int(obj)
-                break
-            except (AttributeError, IndexError, KeyError, TypeError):
-                continue
-        if heads is None:
-            raise LeafError("cannot infer the number of attention heads of the tower")
-        quick = "QuickGELU" in repr(type(getattr(getattr(module, "transformer", None), "resblocks", [None])[0]).__name__) \
-            or any(type(m).__name__ == "QuickGELU" for m in module.modules())
-        eng = LeafEngine(params, heads=heads, quick_gelu=quick)
-        try:
-            model.leaf_engine = eng
-        except Exception:
-            pass
-        return eng
+    if isinstance(model, torch.nn.Module):
+        return bind_module(model)
     raise LeafError("model must be a LeafTextTower, a LeafEngine, or a torch module in open_clip / HF CLIP naming")
 
 
@@ -186,8 +168,12 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
         if Bl > 0 and nl > 0:
             chr2_d = _to_dev(chr2_l.ravel(), dev)
         if shard == "candidates":
-            val1 = loss1.gather(1, best1.long().view(-1, 1)).squeeze(1)
-            _, g1 = D.cross_shard_argmax(val1, best1.long() + jlo, group)     # global index of the best position
+            if nl > 0:
+                val1, idx1 = loss1.gather(1, best1.long().view(-1, 1)).squeeze(1), best1.long() + jlo
+            else:                                                             # n < world size: this rank scores nothing
+                val1 = torch.full((B,), float("-inf"), device=dev)
+                idx1 = torch.full((B,), D.NO_CANDIDATE, dtype=torch.long, device=dev)
+            _, g1 = D.cross_shard_argmax(val1, idx1, group)                   # global index of the best position
             zstar = torch.from_numpy(positions.astype(np.int32)).to(dev).gather(1, g1.view(-1, 1)).squeeze(1)
             pos2_d = zstar.view(-1, 1).expand(Bl, nl).contiguous()            # same position for every candidate
             sel = None
@@ -207,8 +193,13 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
             okv = torch.ones(Bl, dtype=torch.bool, device=dev) if valid2 is None else \
                 valid2.view(Bl, nl).gather(1, g2.view(-1, 1)).squeeze(1).bool()
         if shard == "candidates":
-            val2 = loss2.gather(1, g2.view(-1, 1)).squeeze(1)
-            _, gg2 = D.cross_shard_argmax(val2, g2 + jlo, group)
+            if nl > 0:
+                val2, idx2 = loss2.gather(1, g2.view(-1, 1)).squeeze(1), g2 + jlo
+            else:
+                val2 = torch.full((B,), float("-inf"), device=dev)
+                idx2 = torch.full((B,), D.NO_CANDIDATE, dtype=torch.long, device=dev)
+                okv = torch.zeros(B, dtype=torch.bool, device=dev)
+            _, gg2 = D.cross_shard_argmax(val2, idx2, group)
             owner = torch.zeros(B, dtype=torch.long, device=dev)
             for r in range(G):
                 lo, hi = D.shard_range(n, r, G)
@@ -217,17 +208,22 @@ def attack_text_leaf(model, tokenizer, sentences, anchor_features, device=None, 
             okv = D.broadcast_rows(okv.to(torch.float32), owner, group) > 0.5
             g2 = gg2
         # --- one small D2H per round: the winner indices (+ tokenizer status) ---
-        if Bl > 0 and nl > 0:
-            local = torch.stack([g1, g2, okv.long()]).cpu().numpy()
+        have = Bl > 0 and (nl > 0 or shard == "candidates")
+        if shard == "samples" and G > 1:
+            # ONE all-gather per round: every rank's winner features with its three small integers per sample riding along as
+            # exactly representable floats (indices < 2^24) - [Bl, E + 3] fp32
+            sizes = [D.shard_range(B, r, G)[1] - D.shard_range(B, r, G)[0] for r in range(G)]
+            small = torch.stack([g1, g2, okv.long()], dim=1).to(torch.float32) if have else torch.zeros((Bl, 3), device=dev)
+            both = D.all_gather_cat(torch.cat([feat_l, small], dim=1), sizes, group)
+            best_feat = both[:, :eng.embed_dim].contiguous()
+            allp = both[:, eng.embed_dim:].cpu().numpy().T.astype(np.int64)
+            if have:
+                eng.check_status()
+        elif have:
+            allp, best_feat = torch.stack([g1, g2, okv.long()]).cpu().numpy(), feat_l
             eng.check_status()
         else:
-            local = np.zeros((3, 0), dtype=np.int64)
-        if shard == "samples" and G > 1:
-            sizes = [D.shard_range(B, r, G)[1] - D.shard_range(B, r, G)[0] for r in range(G)]
-            allp = D.all_gather_cat(torch.from_numpy(local.T.copy()).to(dev), sizes, group).cpu().numpy().T
-            best_feat = D.all_gather_cat(feat_l, sizes, group)
-        else:
-            allp, best_feat = local, feat_l
+            allp, best_feat = np.zeros((3, 0), dtype=np.int64), feat_l
         picks[0], picks[1], ok2 = allp[0], allp[1], allp[2].astype(bool)
         zs = positions[np.arange(B), picks[0]]
         cs = chars2[np.arange(B), picks[1]]

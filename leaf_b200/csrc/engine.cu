@@ -64,6 +64,7 @@ struct TrainWs {
   long rows_cap = 0;
   int N = 0, M = 0, T = 0;            // sequences / packed rows / longest sequence of the saved forward
   bool have_forward = false;
+  int64_t generation = 0;           // of the saved forward (leaf_forward_train counts up)
   std::vector<TrainLayer> L;
   float *x_out = nullptr, *dx = nullptr, *dtmp = nullptr, *scratch = nullptr;
   __nv_bfloat16 *pooled = nullptr, *d16 = nullptr, *dx16 = nullptr;
@@ -94,6 +95,7 @@ struct leaf_engine {
   std::vector<LayerW> lw;
   __nv_bfloat16* proj_w = nullptr;    // [E, W] bf16
   TrainWs tw;
+  int64_t train_generation = 0;
   // workspace
   int max_seqs = 0;
   long rows_cap = 0;
@@ -758,7 +760,8 @@ static int launch_ew(leaf_engine* e, size_t n) {      // grid for the grid-strid
   return static_cast<int>(b < cap ? (b ? b : 1) : cap);
 }
 
-extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out, void* stream) {
+extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out,
+                                  int64_t* generation_out, void* stream) {
   if (!e || !tok || !len || !feat_out || N <= 0) return fail(LEAF_ERR_INVALID, "bad argument");
   if (!e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
   if (N > e->tw.max_seqs) return fail(LEAF_ERR_STATE, "training workspace reserved for %d sequences, need %d (leaf_train_reserve)", e->tw.max_seqs, N);
@@ -767,6 +770,7 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
   const int W = e->cfg.width, E = e->cfg.embed_dim;
   int rc;
   t.have_forward = false;
+  t.generation = ++e->train_generation;
   CK(cudaMemcpyAsync(t.tok, tok, static_cast<size_t>(N) * LEAF_CTX * 4, cudaMemcpyDeviceToDevice, st));
   prefix_kernel<<<(N + 7) / 8, 256, 0, st>>>(tok, len, nullptr, nullptr, N, t.pfx, t.own_len);
   scan_lengths_kernel<<<1, 1024, 0, st>>>(t.own_len, N, t.cu, t.total_rows, t.total_rows + 1);
@@ -800,6 +804,7 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
   if ((rc = launch_gemm(e, t.pooled, t.max_seqs + 128, e->proj_w, nullptr, feat_out, E, N, E, W, EPI_F32, 0, nullptr, st))) return rc;
   CK(cudaGetLastError());
   t.have_forward = true;
+  if (generation_out) *generation_out = t.generation;
   return LEAF_OK;
 }
 
@@ -826,10 +831,16 @@ static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x,
 }
 
 // grads mirrors leaf_weight_ptrs_t: fp32 device buffers that are ACCUMULATED into (+=); NULL = parameter is frozen.
-extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_weight_ptrs_t* grads, void* stream) {
+extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* dfeat, int32_t dfeat_rows,
+                             const leaf_weight_ptrs_t* grads, void* stream) {
   if (!e || !dfeat || !grads || !grads->layers) return fail(LEAF_ERR_INVALID, "null argument");
   TrainWs& t = e->tw;
-  if (!t.have_forward) return fail(LEAF_ERR_STATE, "leaf_backward needs a preceding leaf_forward_train");
+  if (!t.have_forward) return fail(LEAF_ERR_STATE, "leaf_backward needs a preceding leaf_forward_train (the activation store is empty or already consumed)");
+  if (generation != 0 && generation != t.generation)
+    return fail(LEAF_ERR_STATE, "the activation store holds forward #%lld, this backward belongs to forward #%lld: the engine keeps ONE "
+                "saved forward (run each encode_text's backward before the next encode_text with gradients enabled)",
+                (long long)t.generation, (long long)generation);
+  if (dfeat_rows != t.N) return fail(LEAF_ERR_INVALID, "dfeat has %d rows, the saved forward has %d sequences", dfeat_rows, t.N);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int W = e->cfg.width, E = e->cfg.embed_dim, N = t.N, M = t.M;
   const long cap = t.rows_cap;
@@ -913,6 +924,7 @@ extern "C" int leaf_backward(leaf_handle_t e, const float* dfeat, const leaf_wei
     e->launches++;
   }
   CK(cudaGetLastError());
+  t.have_forward = false;                              // consumed: dx / dtmp were overwritten, a second backward would be wrong
   return LEAF_OK;
 }
 

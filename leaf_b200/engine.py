@@ -47,7 +47,10 @@ def _canon_state(params: dict):
         out = {"layout": "hf", "tok": params[pre + "embeddings.token_embedding.weight"],
                "pos": params[pre + "embeddings.position_embedding.weight"],
                "lnf_w": params[pre + "final_layer_norm.weight"], "lnf_b": params[pre + "final_layer_norm.bias"],
-               "proj": params[root + "text_projection.weight"], "proj_is_ew": 1, "layers": []}
+               "proj": params.get(root + "text_projection.weight"), "proj_is_ew": 1, "layers": []}
+        if out["proj"] is None:        # CLIPTextModel: the reference reads .pooler_output (utils_attacks.py:49-53) = identity head
+            out["proj"] = torch.eye(out["tok"].shape[1], dtype=torch.float32, device=out["tok"].device)
+            out["proj_synth"] = True
         i = 0
         while (pre + f"encoder.layers.{i}.layer_norm1.weight") in params:
             p = pre + f"encoder.layers.{i}."
@@ -127,6 +130,8 @@ class LeafEngine:
     def _check_tensors(self):
         c = self._canon
         flat = [c["tok"], c["pos"], c["lnf_w"], c["lnf_b"], c["proj"]] + [t for l in c["layers"] for t in l.values()]
+        if not c["layers"]:
+            raise LeafError("no transformer layers found in the parameter dict")
         for t in flat:
             if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise LeafError("tower parameters must be contiguous fp32 CUDA tensors")
@@ -319,19 +324,25 @@ class LeafEngine:
         out = torch.empty((N, self.embed_dim), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(self._lib.leaf_train_reserve(self._h, N))
-            check(self._lib.leaf_forward_train(self._h, _ptr(tok), _ptr(lengths.contiguous()), N, _ptr(out), _stream()))
+            gen = ctypes.c_int64(0)
+            check(self._lib.leaf_forward_train(self._h, _ptr(tok), _ptr(lengths.contiguous()), N, _ptr(out), ctypes.byref(gen), _stream()))
+        self.last_generation = int(gen.value)
         return out
 
-    def backward(self, dfeat: torch.Tensor, grads: dict):
+    def backward(self, dfeat: torch.Tensor, grads: dict, generation: int = 0):
         """loss.backward() through the saved forward: ACCUMULATES into the fp32 tensors of `grads`, a dict in the same
-        naming as the bound parameters (open_clip or HF); entries that are None mark frozen parameters."""
+        naming as the bound parameters (open_clip or HF); entries that are None mark frozen parameters. `generation`
+        (forward_train's self.last_generation) makes the engine refuse to differentiate a forward it no longer holds."""
+        if dfeat.dim() != 2 or dfeat.shape[1] != self.embed_dim:
+            raise LeafError(f"dfeat must be [N, {self.embed_dim}], got {tuple(dfeat.shape)}")
         c = _canon_state(grads)
         for t in [c["tok"], c["pos"], c["lnf_w"], c["lnf_b"], c["proj"]] + [t for l in c["layers"] for t in l.values()]:
             if t is not None and not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
                 raise LeafError("gradient buffers must be contiguous fp32 CUDA tensors")
         keep = self._make_ptrs(c)
         with torch.cuda.device(self.device):
-            check(self._lib.leaf_backward(self._h, _ptr(dfeat.to(torch.float32).contiguous()), ctypes.byref(keep[1]), _stream()))
+            check(self._lib.leaf_backward(self._h, int(generation), _ptr(dfeat.to(torch.float32).contiguous()), int(dfeat.shape[0]),
+                                          ctypes.byref(keep[1]), _stream()))
 
     # ---- K3 ----------------------------------------------------------------------------------------------
     def score(self, feats: torch.Tensor, anchor: torch.Tensor, B: int, n: int, objective: str = "l2", want_loss=False):
@@ -421,3 +432,67 @@ class LeafEngine:
     def last_rows(self) -> int:
         """Packed token rows (sum of argmax(ids)+1) of the last encode; synchronises."""
         return int(self._lib.leaf_last_rows(self._h))
+
+
+# ---- binding a live torch module (the reference's `model` argument) ----------------------------------------------------
+def _text_config(module):
+    """(heads, quick_gelu, ln_eps) of an HF CLIPTextModel / CLIPTextModelWithProjection / CLIPModel from its config, or
+    None when `module` is not an HF model."""
+    cfg = getattr(module, "config", None)
+    cfg = getattr(cfg, "text_config", None) or cfg
+    act = getattr(cfg, "hidden_act", None)
+    if cfg is None or act is None or not hasattr(cfg, "num_attention_heads"):
+        return None
+    if act not in ("quick_gelu", "gelu"):
+        raise LeafError(f"unsupported text-tower activation {act!r} (the engine has nn.GELU and QuickGELU)")
+    return int(cfg.num_attention_heads), act == "quick_gelu", float(getattr(cfg, "layer_norm_eps", 1e-5))
+
+
+def _open_clip_config(module):
+    """(heads, quick_gelu, ln_eps) of an open_clip CLIP / CustomTextCLIP / TextTransformer-shaped module: heads from the first
+    residual block's nn.MultiheadAttention, the activation from the class of the MLP's activation module
+    (transformer.py:33-36 QuickGELU vs nn.GELU; model.py:192)."""
+    text = getattr(module, "text", module)
+    blocks = getattr(getattr(text, "transformer", None), "resblocks", None)
+    if blocks is None or len(blocks) == 0:
+        raise LeafError("cannot find transformer.resblocks in the module (open_clip naming expected)")
+    blk = blocks[0]
+    heads = getattr(getattr(blk, "attn", None), "num_heads", None)
+    if heads is None:
+        raise LeafError("cannot infer the number of attention heads of the tower")
+    acts = {type(m).__name__ for m in blk.modules()}
+    quick = bool(acts & {"QuickGELU", "QuickGELUActivation"})
+    if not quick and not acts & {"GELU", "GELUActivation"}:
+        raise LeafError(f"cannot tell the MLP activation of the tower (module classes: {sorted(acts)})")
+    eps = float(getattr(getattr(blk, "ln_1", None), "eps", 1e-5))
+    return int(heads), quick, eps
+
+
+def bind_module(model) -> LeafEngine:
+    """Engine for a live torch module in open_clip or HF naming (also behind a DDP-style `.module` holder). Created on first
+    use and cached on the module as `leaf_engine`; later calls re-cast the engine's bf16 operand copies when any bound
+    parameter changed in place (optimizer step) and rebind when the parameters moved. HF layouts switch the tokenizer
+    kernel to CLIPTokenizer's rules (the reference drives HF models with tokenizer_wrapper, utils_attacks.py:67-71,
+    eval_textfare.py:100-127)."""
+    module = model.module if isinstance(getattr(model, "module", None), torch.nn.Module) else model
+    eng = getattr(module, "leaf_engine", None)
+    if isinstance(eng, LeafEngine) and getattr(module, "_leaf_self_managed", False):
+        return eng                                                           # LeafTextTower refreshes its own engine
+    live = module.state_dict(keep_vars=True)
+    c = _canon_state({k: v for k, v in live.items() if torch.is_tensor(v)})
+    flat = [c["tok"], c["pos"], c["lnf_w"], c["lnf_b"]] + ([] if c.get("proj_synth") else [c["proj"]]) + \
+           [t for l in c["layers"] for t in l.values()]
+    ptrs = tuple(t.data_ptr() for t in flat)
+    version = sum(t._version for t in flat)
+    if isinstance(eng, LeafEngine) and getattr(eng, "_bound_ptrs", None) == ptrs:
+        if eng._bound_version != version:
+            eng.refresh_weights()
+            eng._bound_version = version
+        return eng
+    heads, quick, eps = _text_config(module) or _open_clip_config(module)
+    eng = LeafEngine({k: v.detach() for k, v in live.items() if torch.is_tensor(v)}, heads=heads, quick_gelu=quick, ln_eps=eps)
+    if c["layout"] == "hf":
+        eng.set_tokenizer_mode(True)
+    eng._bound_ptrs, eng._bound_version = ptrs, version
+    object.__setattr__(module, "leaf_engine", eng)                           # a plain attribute, not a registered submodule
+    return eng

@@ -28,19 +28,22 @@ def no_weight_decay(name: str, ndim: int) -> bool:
 class _EncodeTextTrain(torch.autograd.Function):
     """encode_text under autograd: forward = leaf_forward_train, backward = leaf_backward, which ACCUMULATES straight into
     the parameters' .grad (views of the tower's flat gradient buffer) - no per-parameter temporaries, no 390 tiny
-    add kernels. The parameters are inputs of the Function only so that autograd knows the output needs a backward."""
+    add kernels. The engine keeps ONE saved forward: a second encode_text with gradients enabled before this output's
+    backward makes that backward raise LeafError (generation check) instead of differentiating the wrong activations. The parameters are inputs of the Function only so that autograd knows the output needs a backward."""
 
     @staticmethod
     def forward(ctx, tower, tok, *params):
         ctx.tower = tower
-        return tower.leaf_engine.forward_train(tok)
+        out = tower.leaf_engine.forward_train(tok)
+        ctx.generation = tower.leaf_engine.last_generation
+        return out
 
     @staticmethod
     def backward(ctx, dfeat):
         tower = ctx.tower
         tower.attach_grads()
         grads = {k: (p.grad if p.requires_grad else None) for k, p in tower.named_tower_parameters()}
-        tower.leaf_engine.backward(dfeat, grads)
+        tower.leaf_engine.backward(dfeat, grads, ctx.generation)
         return (None, None) + (None,) * len(grads)
 
 
@@ -60,6 +63,8 @@ def text_tower_state_dict(state_dict: dict) -> dict:
 
 
 class LeafTextTower(torch.nn.Module):
+    _leaf_self_managed = True            # engine.bind_module: this module refreshes its own engine (refresh())
+
     def __init__(self, state_dict: dict, heads: int, quick_gelu: bool = False, device="cuda"):
         super().__init__()
         state_dict = text_tower_state_dict(state_dict)

@@ -136,6 +136,36 @@ def _worker(rank, world, port, out):
     idx = torch.tensor([4, 0, 9]) if rank == 0 else torch.tensor([2, 6, 11])
     gv, gi = D.cross_shard_argmax(val, idx)
     res["argmax"] = (gv.tolist(), gi.tolist())
+    # a NaN score never wins over a number, an empty shard (NO_CANDIDATE) never wins at all; the packed pair survives the
+    # round trip bit for bit (negative scores, -0.0, indices up to 2^31 - 2)
+    val = torch.tensor([float("nan"), -3.5, float("-inf")]) if rank == 0 else torch.tensor([1.0, float("-inf"), float("nan")])
+    idx = torch.tensor([0, 7, 3]) if rank == 0 else torch.tensor([5, D.NO_CANDIDATE, 2])
+    gv, gi = D.cross_shard_argmax(val, idx)
+    res["argmax_nan"] = (gv.tolist(), gi.tolist())
+    pv, pi = torch.tensor([-0.0, -1.25e-30, 3.4e38, float("inf")]), torch.tensor([0, 2 ** 31 - 2, 49, D.NO_CANDIDATE])
+    uv, ui = D.unpack_score_index(D.pack_score_index(pv, pi))
+    res["pack"] = bool(torch.equal(uv.view(torch.int32), pv.view(torch.int32)) and torch.equal(ui, pi))
+    # broadcast_rows selects the owner's rows: NaN / Inf in rows a rank does not own must not leak
+    rows = torch.tensor([[1.0, 2.0], [float("nan"), float("inf")]]) if rank == 0 else torch.tensor([[float("inf"), float("nan")], [3.0, 4.0]])
+    res["bcast"] = D.broadcast_rows(rows, torch.tensor([0, 1])).tolist()
+    # fewer candidates than ranks (n = 1 < world size): rank 1 scores nothing and must still take part in every collective
+    eng = OracleEngine(sd, cfg.heads)
+    c = g["cases"][0]
+    np.random.seed(77)
+    _, adv1 = attack_text_leaf(eng, None, c["captions"][:3], torch.from_numpy(z["anchor_0"])[:3].clone(), "cpu", n=1, k=2,
+                               shard="candidates")
+    np.random.seed(77)
+    _, adv0 = attack_text_leaf(OracleEngine(sd, cfg.heads), None, c["captions"][:3], torch.from_numpy(z["anchor_0"])[:3].clone(),
+                               "cpu", n=1, k=2)
+    res["n_lt_world"] = (adv1 == adv0, eng.encoded_rows)
+    # fewer samples than ranks (B = 1): rank 1 attacks nothing in the sample-sharded mode
+    np.random.seed(78)
+    _, adv1 = attack_text_leaf(OracleEngine(sd, cfg.heads), None, c["captions"][:1], torch.from_numpy(z["anchor_0"])[:1].clone(),
+                               "cpu", n=6, k=1, shard="samples")
+    np.random.seed(78)
+    _, adv0 = attack_text_leaf(OracleEngine(sd, cfg.heads), None, c["captions"][:1], torch.from_numpy(z["anchor_0"])[:1].clone(),
+                               "cpu", n=6, k=1)
+    res["b_lt_world"] = adv1 == adv0
     for mode in ("samples", "candidates"):
         for ci in (1, 3):                             # k=1 n=50 and k=2 n=20
             c = g["cases"][ci]
@@ -156,6 +186,10 @@ def test_sharded_modes_equal_the_unsharded_run_gloo_world2():
     for rank in (0, 1):
         res = out[rank]
         assert res["argmax"] == ([5.0, 2.0, 7.0], [2, 6, 9])
+        assert res["argmax_nan"][1] == [5, 7, 3] and res["argmax_nan"][0][:2] == [1.0, -3.5]
+        assert res["pack"]
+        assert res["bcast"] == [[1.0, 2.0], [3.0, 4.0]]
+        assert res["n_lt_world"][0] and res["b_lt_world"]
         for mode in ("samples", "candidates"):
             for ci in (1, 3):
                 adv, err, rows = res[(mode, ci)]
@@ -166,6 +200,7 @@ def test_sharded_modes_equal_the_unsharded_run_gloo_world2():
     full = 2 * c["k"] * (c["B"] * c["n"] + c["B"])
     assert out[0][("samples", 1)][2] + out[1][("samples", 1)][2] == full
     assert out[0][("candidates", 1)][2] < 0.6 * full
+    assert out[0]["n_lt_world"][1] == 0 and out[1]["n_lt_world"][1] > 0      # n = 1: rank 0 held the empty shard [0, 0)
 
 
 def test_fast_draw_is_np_random_choice():

@@ -63,6 +63,34 @@ def test_backward_matches_autograd(name, quick):
     assert err(getattr(tower, tower._names[k0]).grad, 2 * vjp[k0])[0] <= 3e-2
 
 
+def test_one_forward_one_backward_is_enforced():
+    """The engine keeps ONE saved forward. A backward through an output whose activations were overwritten by a later
+    encode_text, a second backward through the same output, or a dfeat of the wrong height must raise - never
+    differentiate the wrong activations or read out of bounds."""
+    from leaf_b200 import LeafError, synth
+    from leaf_b200.tower import LeafTextTower
+    tower = LeafTextTower.random("tiny", seed=1).trainable()
+    eng = tower.leaf_engine
+    tok_a, tok_b = tower.tokenizer(synth.make_captions(4, seed=1)), tower.tokenizer(synth.make_captions(6, seed=2))
+    fa = tower.encode_text(tok_a)
+    fb = tower.encode_text(tok_b)                          # overwrites fa's activations
+    with pytest.raises(LeafError, match="ONE saved forward"):
+        fa.sum().backward()
+    fb.sum().backward()                                    # the latest forward is still intact
+    g1 = tower.flat_grads.clone()
+    assert float(g1.abs().max()) > 0
+    with pytest.raises(LeafError, match="consumed"):       # its store is gone now
+        eng.backward(torch.ones_like(fb), {k: p.grad for k, p in tower.named_tower_parameters()}, eng.last_generation)
+    f = eng.forward_train(tok_a)
+    grads = {k: p.grad for k, p in tower.named_tower_parameters()}
+    with pytest.raises(LeafError, match="rows"):
+        eng.backward(torch.ones((3, f.shape[1]), device="cuda"), grads, eng.last_generation)
+    with pytest.raises(LeafError):
+        eng.backward(torch.ones((4, f.shape[1] + 8), device="cuda"), grads, eng.last_generation)
+    eng.backward(torch.ones_like(f), grads, eng.last_generation)
+    assert not torch.equal(tower.flat_grads, g1)
+
+
 def test_backward_hf_layout():
     from leaf_b200 import synth
     from leaf_b200.engine import LeafEngine

@@ -1,0 +1,300 @@
+"""The drop-in boundary with REAL torch modules: attack_text_leaf / the eval attacks take whatever the
+reference's callers pass as `model` - an open_clip-named CLIP behind DDP's `.module` (utils_AT.py:307), an HF CLIPModel /
+CLIPTextModelWithProjection / CLIPTextModel with a patched encode_text (utils_attacks.py:49-65, eval_textfare.py:100-127) -
+and must bind it correctly: activation from the config / module class (QuickGELU vs nn.GELU), heads, LayerNorm eps, the HF
+tokenizer rules for HF layouts, live parameters re-cast after an in-place update.
+
+Checked against the MODULE'S OWN fp32 CUDA forward (cos >= 0.999) and against the oracle attack loop driven by that forward
+(selected-candidate agreement on non-tied decisions), plus the headline ViT-H-14 24-layer tower and the full-size attack
+against the fp32 oracle tower evaluated with plain torch ops on the same GPU."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+COS_MIN = 0.999
+LOSS_RTOL = 1e-2
+
+
+def _cos(a, b):
+    return torch.nn.functional.cosine_similarity(a.double(), b.double(), dim=-1)
+
+
+# ---- a minimal text tower in open_clip's module / parameter naming (model.py:186-215, transformer.py:210-366) ---------------
+class QuickGELU(torch.nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class _Block(torch.nn.Module):
+    def __init__(self, W, heads, quick):
+        super().__init__()
+        self.ln_1 = torch.nn.LayerNorm(W)
+        self.attn = torch.nn.MultiheadAttention(W, heads, batch_first=True)
+        self.ln_2 = torch.nn.LayerNorm(W)
+        self.mlp = torch.nn.Sequential(OrderedDict([("c_fc", torch.nn.Linear(W, 4 * W)), ("gelu", QuickGELU() if quick else torch.nn.GELU()),
+                                                    ("c_proj", torch.nn.Linear(4 * W, W))]))
+
+    def forward(self, x, mask):
+        h = self.ln_1(x)
+        x = x + self.attn(h, h, h, need_weights=False, attn_mask=mask)[0]
+        return x + self.mlp(self.ln_2(x))
+
+
+class _Transformer(torch.nn.Module):
+    def __init__(self, W, layers, heads, quick):
+        super().__init__()
+        self.resblocks = torch.nn.ModuleList([_Block(W, heads, quick) for _ in range(layers)])
+
+
+class OpenClipNamedTower(torch.nn.Module):
+    def __init__(self, cfg, quick=False, seed=0):
+        super().__init__()
+        from leaf_b200 import synth
+        W = cfg.width
+        self.token_embedding = torch.nn.Embedding(cfg.vocab_size, W)
+        self.positional_embedding = torch.nn.Parameter(torch.empty(cfg.context_length, W))
+        self.transformer = _Transformer(W, cfg.layers, cfg.heads, quick)
+        self.ln_final = torch.nn.LayerNorm(W)
+        self.text_projection = torch.nn.Parameter(torch.empty(W, cfg.embed_dim))
+        self.logit_scale = torch.nn.Parameter(torch.ones([]))                       # present in CLIP, not a tower parameter
+        self.register_buffer("attn_mask", torch.full((cfg.context_length, cfg.context_length), float("-inf")).triu_(1), persistent=False)
+        self.load_state_dict(synth.random_tower_state_dict(cfg, seed=seed, exact_numpy=True), strict=False)
+
+    def encode_text(self, text, normalize=False):                                   # model.py:269-284
+        x = self.token_embedding(text) + self.positional_embedding[:text.shape[1]]
+        for blk in self.transformer.resblocks:
+            x = blk(x, self.attn_mask[:text.shape[1], :text.shape[1]])
+        x = self.ln_final(x)
+        x = x[torch.arange(x.shape[0]), text.argmax(dim=-1)] @ self.text_projection
+        return torch.nn.functional.normalize(x, dim=-1) if normalize else x
+
+
+class _DDPLike(torch.nn.Module):                 # what train_AT_text_only.py:310-317 hands to the attack under --distributed
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+
+def _hf_text_config(quick, layers=3, W=256, heads=4, E=128):
+    from transformers import CLIPTextConfig
+    return CLIPTextConfig(vocab_size=49408, hidden_size=W, intermediate_size=4 * W, num_hidden_layers=layers, num_attention_heads=heads,
+                          max_position_embeddings=77, hidden_act="quick_gelu" if quick else "gelu", projection_dim=E,
+                          eos_token_id=49407, bos_token_id=49406, pad_token_id=49407)
+
+
+def _randomize(module, seed):
+    """HF's default init leaves LayerNorm at (1, 0) and biases at 0: give every parameter a value that matters."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.dim() >= 2:
+                p.copy_(torch.randn(p.shape, generator=g) * (0.02 if "embedding" in name else p.shape[-1] ** -0.5))
+            elif "norm" in name and name.endswith("weight"):
+                p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+            else:
+                p.copy_(0.02 * torch.randn(p.shape, generator=g))
+    return module
+
+
+def _hf_features(module, ids):
+    """What the reference's three wrappers read (utils_attacks.py:49-65)."""
+    out = module.get_text_features(ids) if hasattr(module, "get_text_features") else module(ids)
+    if torch.is_tensor(out):
+        return out
+    return out.text_embeds if getattr(out, "text_embeds", None) is not None else out.pooler_output
+
+
+def _attack_agreement(model, encode, tokenize, caps, n, seed, quick_check=None):
+    """attack_text_leaf(model) against the oracle loop over `encode` (fp32): winners must agree wherever both phase
+    decisions of the oracle are clear of the loss tolerance."""
+    from leaf_b200 import attack_text_leaf
+    from oracle import leaf_oracle as O
+    with torch.no_grad():
+        anchor = encode(tokenize(caps), False)
+        anchor = anchor + 0.05 * anchor.norm(dim=-1, keepdim=True) * torch.randn(anchor.shape, generator=torch.Generator().manual_seed(seed))
+        np.random.seed(seed)
+        trace = {}
+        _, want = O.attack_text_leaf_oracle(encode, tokenize, caps, anchor.clone(), objective="l2", n=n, k=1, trace=trace)
+        np.random.seed(seed)
+        feats, adv = attack_text_leaf(model, None, caps, anchor.clone().cuda(), "cuda", objective="l2", n=n, k=1)
+    r = trace["rounds"][0]
+    total = agree = 0
+    for b in range(len(caps)):
+        clear = True
+        for loss in (r["loss1"][b], r["loss2"][b]):
+            top = torch.topk(loss, 2).values
+            clear &= bool((top[0] - top[1]).abs() > LOSS_RTOL * top[0].abs())
+        if clear:
+            total += 1
+            agree += int(adv[b] == want[b])
+    # the returned features are the winners' own, by the module's forward
+    own = encode(tokenize(adv), False)
+    assert _cos(feats.cpu(), own).min() >= COS_MIN
+    return agree, total
+
+
+@pytest.mark.parametrize("quick", [False, True])
+def test_hf_text_model_with_projection_is_a_drop_in(quick):
+    from transformers import CLIPTextModelWithProjection
+    from leaf_b200 import synth
+    from leaf_b200.engine import bind_module
+    from oracle import leaf_oracle as O
+    hf = _randomize(CLIPTextModelWithProjection(_hf_text_config(quick)), seed=5 + quick).eval().cuda()
+    eng = bind_module(hf)
+    assert eng.hf_tokenizer and eng.heads == 4 and eng.layers == 3 and bind_module(hf) is eng
+    caps = synth.make_captions(10, seed=1) + synth.make_captions(2, seed=1, kind="dense-77") + ["a &amp; b", "x <|endoftext|> y", ""]
+    otok = O.OracleTokenizer(hf=True)
+    ids = eng.tokenize_hf(caps)
+    assert torch.equal(ids.cpu(), otok.hf_call(caps))                               # CLIPTokenizer's rules, not SimpleTokenizer's
+    with torch.no_grad():
+        want = _hf_features(hf, ids)
+    got = eng.encode_hf_tokens(ids)
+    assert _cos(got, want).min() >= COS_MIN, _cos(got, want).min().item()
+    assert (got - want).norm() / want.norm() < 1e-2
+    # the wrong activation must NOT pass this check (what the class-name test of round 1 bound silently)
+    from leaf_b200.engine import LeafEngine
+    wrong = LeafEngine({k: v.detach() for k, v in hf.state_dict(keep_vars=True).items()}, heads=4, quick_gelu=not quick)
+    err_right = ((got - want).norm() / want.norm()).item()
+    err_wrong = ((wrong.encode_hf_tokens(ids) - want).norm() / want.norm()).item()
+    assert err_wrong > 3 * err_right, (err_right, err_wrong)
+    encode = lambda t, normalize: _hf_features(hf, t.cuda()).cpu()
+    agree, total = _attack_agreement(hf, encode, otok.hf_call, caps[:10] + synth.make_captions(14, seed=8), n=30, seed=3)
+    assert total >= 4 and agree == total, (agree, total)
+
+
+def test_hf_clip_model_and_text_model_are_drop_ins():
+    """CLIPModel (get_text_features, eval_textfare.py:100-127) and the projection-less CLIPTextModel (pooler_output,
+    utils_attacks.py:49-53: bound with an identity head)."""
+    from transformers import CLIPConfig, CLIPModel, CLIPTextModel, CLIPVisionConfig
+    from leaf_b200 import synth
+    from leaf_b200.engine import bind_module
+    from oracle import leaf_oracle as O
+    tcfg = _hf_text_config(True, layers=2, W=128, heads=2, E=64)
+    vcfg = CLIPVisionConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=2, image_size=32, patch_size=16)
+    otok = O.OracleTokenizer(hf=True)
+    caps = synth.make_captions(8, seed=2)
+    for hf in (CLIPModel(CLIPConfig(text_config=tcfg.to_dict(), vision_config=vcfg.to_dict(), projection_dim=64)), CLIPTextModel(tcfg)):
+        hf = _randomize(hf, seed=9).eval().cuda()
+        eng = bind_module(hf)
+        assert eng.hf_tokenizer and eng.embed_dim == (64 if hasattr(hf, "get_text_features") else 128)
+        ids = eng.tokenize_hf(caps)
+        with torch.no_grad():
+            want = _hf_features(hf, ids)
+        got = eng.encode_hf_tokens(ids)
+        assert _cos(got, want).min() >= COS_MIN, (type(hf).__name__, _cos(got, want).min().item())
+        encode = lambda t, normalize, hf=hf: _hf_features(hf, t.cuda()).cpu()
+        agree, total = _attack_agreement(hf, encode, otok.hf_call, caps + synth.make_captions(8, seed=12), n=20, seed=4)
+        assert total >= 2 and agree == total, (type(hf).__name__, agree, total)
+
+
+@pytest.mark.parametrize("quick", [False, True])
+def test_open_clip_named_module_behind_a_ddp_holder(quick):
+    from leaf_b200 import attack_text_charmer_inference, synth
+    from leaf_b200.engine import bind_module
+    from oracle import leaf_oracle as O
+    cfg = synth.TOWERS["small"]
+    tower = OpenClipNamedTower(cfg, quick=quick, seed=31).eval().cuda()
+    ddp = _DDPLike(tower)
+    eng = bind_module(ddp)
+    assert not getattr(eng, "hf_tokenizer", False) and eng.heads == cfg.heads and bind_module(tower) is eng
+    caps = synth.make_captions(10, seed=3) + ["a &amp; b"]
+    otok = O.OracleTokenizer()
+    tok = eng.tokenize(caps)
+    assert torch.equal(tok.cpu(), otok(caps))
+    with torch.no_grad():
+        want = tower.encode_text(tok)
+    got = eng.encode_tokens(tok)
+    assert _cos(got, want).min() >= COS_MIN, _cos(got, want).min().item()
+    # the oracle tower on the module's state dict agrees with the module itself (pins this test's fixture module)
+    sd = {k: v.detach().cpu() for k, v in tower.state_dict().items()}
+    assert torch.allclose(O.encode_text(sd, tok.cpu(), cfg.heads, quick_gelu=quick), want.cpu(), atol=1e-4)
+    encode = lambda t, normalize: tower.encode_text(t.cuda(), normalize).cpu()
+    agree, total = _attack_agreement(ddp, encode, otok, caps[:10] + synth.make_captions(14, seed=8), n=30, seed=5)
+    assert total >= 4 and agree == total, (agree, total)
+    # an in-place parameter update (optimizer.step()) is picked up on the next call: the engine re-casts its operand copies
+    with torch.no_grad():
+        for p in tower.parameters():
+            if p.dim() >= 2:
+                p.add_(0.02 * p.std() * torch.randn(p.shape, device=p.device, generator=torch.Generator(device="cuda").manual_seed(1)))
+        want2 = tower.encode_text(tok)
+    assert _cos(want2, want).min() < 0.9999                                          # the update moved the features
+    assert bind_module(ddp) is eng
+    assert _cos(eng.encode_tokens(tok), want2).min() >= COS_MIN
+    adv, dist_ = attack_text_charmer_inference(ddp, None, caps[0], want2[:1].clone(), "cuda", n=5, k=1)
+    assert dist_ == 1 and adv != caps[0]
+
+
+def _oracle_tower_cuda(sd, tok, heads, chunk=512):
+    from oracle import leaf_oracle as O
+    out = []
+    with torch.no_grad():
+        for s in range(0, tok.shape[0], chunk):
+            out.append(O.encode_text_device(sd, tok[s:s + chunk], heads))
+    return torch.cat(out)
+
+
+def test_vit_h_24_layers_tower_and_attack_vs_fp32_oracle():
+    """The headline shape against the oracle, not against itself: ViT-H-14 (24 layers, W = 1024) on typical and dense-77
+    rows, fp32 oracle tower on the HOST for 10 rows, then the whole B = 128, rho = 50 attack step against the same oracle
+    lines evaluated by torch in fp32 on the GPU (TF32 off): every candidate's embedding (cos >= 0.999) and TextFARE loss
+    (rel. err <= 1e-2), and the selection of both phases (>= 99 % on non-tied scores)."""
+    from leaf_b200 import synth
+    from leaf_b200.tower import LeafTextTower
+    from oracle import leaf_oracle as O
+    assert not torch.backends.cuda.matmul.allow_tf32
+    cfg = synth.TOWERS["ViT-H-14"]
+    tower = LeafTextTower.random("ViT-H-14", seed=0)
+    eng = tower.leaf_engine
+    sd = tower.open_clip_state_dict()
+    otok = O.OracleTokenizer()
+    rows = synth.make_captions(6, seed=2) + synth.make_captions(3, seed=2, kind="dense-77") + ["a"]
+    tok = tower.tokenizer(rows)
+    assert torch.equal(tok.cpu(), otok(rows))
+    f = tower.encode_text(tok)
+    want_host = O.encode_text({k: v.cpu() for k, v in sd.items()}, tok.cpu(), cfg.heads)
+    want_dev = _oracle_tower_cuda(sd, tok, cfg.heads)
+    assert torch.allclose(want_dev.cpu(), want_host, atol=2e-4, rtol=1e-4)           # the same oracle lines on either device
+    assert _cos(f.cpu(), want_host).min() >= COS_MIN, _cos(f.cpu(), want_host).min().item()
+    assert (f.cpu() - want_host).norm() / want_host.norm() < 1e-2
+
+    B, n = 128, 50
+    caps = synth.make_captions(B - 8, seed=100) + synth.make_captions(8, seed=100, kind="dense-77")
+    frozen = synth.perturbed_copy(sd, seed=1, std=1e-3)
+    anchor = _oracle_tower_cuda(frozen, tower.tokenizer(caps), cfg.heads)
+    del frozen
+    rs = np.random.RandomState(0)
+    pos = np.stack([rs.choice(range(2 * len(S) + 1), size=n, replace=n > 2 * len(S) + 1) for S in caps]).astype(np.int32)
+    chars = np.array(synth.V_DEFAULT, dtype=np.int32)[np.stack([rs.choice(range(96), size=n, replace=False) for _ in caps])]
+    d, o = eng.upload_captions(caps)
+    pos_d, chr_d = torch.from_numpy(pos).cuda(), torch.from_numpy(chars).cuda()
+    space = torch.full((B * n,), 32, dtype=torch.int32, device="cuda")
+    sel = None
+    stats = []
+    for phase in (1, 2):
+        tk, ln, base = eng.expand_tokenize(d, o, B, n, pos=pos_d, chr_=space if phase == 1 else chr_d, sel=sel)
+        feats = eng.encode_tokens(tk, ln, False, base, (B * n, n), trim=True)
+        best, _, loss = eng.score(feats, anchor, B, n, "l2", want_loss=True)
+        if phase == 1:
+            strings = [O.edit_sentence(S, int(z), 32) for b, S in enumerate(caps) for z in pos[b]]
+        else:
+            zs = pos[np.arange(B), sel.cpu().numpy()]
+            strings = [O.edit_sentence(S, int(zs[b]), int(c)) for b, S in enumerate(caps) for c in chars[b]]
+        want_tok = otok(strings)
+        assert torch.equal(tk[:B * n].cpu().long(), want_tok)                        # token ids bit-exact at full size
+        want_f = _oracle_tower_cuda(sd, want_tok.cuda(), cfg.heads)
+        want_loss = ((want_f.view(B, n, -1) - anchor.view(B, 1, -1)) ** 2).sum(-1)
+        cos = _cos(feats[:B * n], want_f)
+        rel = (loss - want_loss).abs() / want_loss.abs().clamp_min(1e-12)
+        top = torch.topk(want_loss, 2, dim=-1).values
+        nontied = (top[:, 0] - top[:, 1]).abs() > LOSS_RTOL * top[:, 0].abs()
+        agree = (best.long() == want_loss.argmax(-1))[nontied].float().mean().item()
+        stats.append((phase, cos.min().item(), rel.max().item(), int(nontied.sum()), agree))
+        assert cos.min() >= COS_MIN, stats
+        assert rel.max() <= LOSS_RTOL, stats
+        assert int(nontied.sum()) >= B // 4 and agree >= 0.99, stats
+        sel = want_loss.argmax(-1).to(torch.int32)                                   # phase 2 on the ORACLE's positions: same candidate sets
+    print("ViT-H full-size parity (phase, cos_min, loss_rel_max, non-tied, agreement):", stats)
