@@ -382,50 +382,70 @@ CN_HD int cn_count_words(const CnTables& T, const uint8_t* text, int n, uint8_t*
     for (int k = s; k < e; ++k) buf_a[k - s] = text[k];
     ovf |= cn_treebank_count(T, buf_a, e - s, buf_b, found);
   };
+  // punkt.py _period_context_fmt: a sentence-end character followed by a non-word character, or by whitespace and a token
+  auto end_context = [&](int i) {
+    const uint8_t c = text[i];
+    if (!(c == '.' || c == '?' || c == '!') || i + 1 >= n) return false;
+    if (cn_nonword(text[i + 1])) return true;
+    int j = i + 1;
+    while (j < n && cn_ws(text[j])) ++j;
+    return j > i + 1 && j < n;
+  };
+  bool pending = false;      // a break decided at an earlier end character of the same whitespace-delimited word
   for (int i = 0; i < n;) {
     const uint8_t c = text[i];
-    if ((c == '.' || c == '?' || c == '!') && i + 1 < n) {
+    if (end_context(i)) {
       const uint8_t nx = text[i + 1];
       int j = i + 1;
       while (j < n && cn_ws(text[j])) ++j;
       const bool after_ws = j > i + 1 && j < n;
-      if (cn_nonword(nx) || after_ws) {
-        bool brk = true;
-        if (c == '.') {
-          if ((i > 0 && text[i - 1] == '.') || nx == '.') {
-            brk = false;
-          } else {
-            int s = i;
-            while (s > 0 && !cn_ws(text[s - 1]) && !cn_nonword(text[s - 1])) --s;
-            const int sl = i - s;
-            if (sl > 0) {
-              int hy = i;                                                  // the part after the last '-'
-              while (hy > s && text[hy - 1] != '-') --hy;
-              if (cn_lookup(T.abbrev, T.abbrev_bits, cn_fnv(text + s, sl)) ||
-                  (hy > s && cn_lookup(T.abbrev, T.abbrev_bits, cn_fnv(text + hy, i - hy))))
-                brk = false;
-              else if (sl == 1 && ((text[s] >= 'a' && text[s] <= 'z') || (text[s] >= 'A' && text[s] <= 'Z')))
-                brk = false;
-              else if (cn_is_number(text + s, sl))
-                brk = false;
-            }
+      bool brk = true;
+      if (c == '.') {
+        if ((i > 0 && text[i - 1] == '.') || nx == '.') {
+          brk = false;
+        } else {
+          int s = i;
+          while (s > 0 && !cn_ws(text[s - 1]) && !cn_nonword(text[s - 1])) --s;
+          const int sl = i - s;
+          if (sl > 0) {
+            int hy = i;                                                  // the part after the last '-'
+            while (hy > s && text[hy - 1] != '-') --hy;
+            if (cn_lookup(T.abbrev, T.abbrev_bits, cn_fnv(text + s, sl)) ||
+                (hy > s && cn_lookup(T.abbrev, T.abbrev_bits, cn_fnv(text + hy, i - hy))))
+              brk = false;
+            else if (sl == 1 && ((text[s] >= 'a' && text[s] <= 'z') || (text[s] >= 'A' && text[s] <= 'Z')))
+              brk = false;
+            else if (cn_is_number(text + s, sl))
+              brk = false;
           }
         }
-        if (brk) {
-          int end = i + 1;
-          int start = after_ws ? j : i + 1;
-          int k = start;
-          while (k < n && cn_in(text[k], "\"')]}")) ++k;
-          if (k > start && (k == n || cn_ws(text[k]) || (k + 1 < n && text[k] == '-' && text[k + 1] == '-'))) {
-            end = k;
-            while (k < n && cn_ws(text[k])) ++k;
-            start = k;
-          }
-          sentence(last, end);
-          last = start;
-          i = start > i + 1 ? start : i + 1;
-          continue;
+      }
+      // potential ends inside ONE word are one decision, taken at the last of them (NLTK >= 3.6.6,
+      // PunktSentenceTokenizer._match_potential_end_contexts; oracle/nltk_restate.py::sent_split)
+      bool later = false;
+      for (int k = i + 1; k < n && !cn_ws(text[k]); ++k)
+        if (end_context(k)) { later = true; break; }
+      if (later) {
+        pending |= brk;
+        ++i;
+        continue;
+      }
+      brk |= pending;
+      pending = false;
+      if (brk) {
+        int end = i + 1;
+        int start = after_ws ? j : i + 1;
+        int k = start;
+        while (k < n && cn_in(text[k], "\"')]}")) ++k;
+        if (k > start && (k == n || cn_ws(text[k]) || (k + 1 < n && text[k] == '-' && text[k + 1] == '-'))) {
+          end = k;
+          while (k < n && cn_ws(text[k])) ++k;
+          start = k;
         }
+        sentence(last, end);
+        last = start;
+        i = start > i + 1 ? start : i + 1;
+        continue;
       }
     }
     ++i;

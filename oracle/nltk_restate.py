@@ -6,9 +6,12 @@
         la = len(W & set(word_tokenize(a.lower())))       per candidate
         valid = la < lo
 
-PARITY UNPINNED. NLTK (unpinned in /root/reference/requirements.txt) and its `words` / `punkt` data are not installed
-in this image and cannot be fetched, so nothing here could be checked against the real thing. The functions below
-RESTATE the published algorithm of `nltk.word_tokenize` (NLTK 3.8.x):
+PARITY: PINNED TO NLTK'S PUBLISHED VECTORS ONLY. NLTK (unpinned in /root/reference/requirements.txt) and its `words` /
+`punkt` data are not installed in this image and cannot be fetched, so this module was never run against a live NLTK.
+What pins it: the 35 input/output pairs NLTK publishes in its own docstrings, doctests and unit tests
+(tests/golden/nltk_published_vectors.json; 34 reproduced, the one known divergence is a Capitalised-text case outside
+the reference's lower-cased domain - tests/test_constrain_cpu.py). The functions below RESTATE the published algorithm of
+`nltk.word_tokenize` (NLTK 3.8.x):
 
   * `NLTKWordTokenizer.tokenize`  (nltk/tokenize/destructive.py): the regular-expression pipeline is written out below
     substitution by substitution, in NLTK's order, with Python's `re` - the same engine NLTK runs them on.
@@ -18,6 +21,12 @@ RESTATE the published algorithm of `nltk.word_tokenize` (NLTK 3.8.x):
     ends a sentence; '?' and '!' always do) with a caller-supplied abbreviation set, plus the outcome of its second pass
     for lower-cased text (initials and numbers followed by a lower-case token do not end a sentence). Captions are
     almost always one sentence, where this step is the identity.
+    Known, unmeasurable-here divergences from Punkt with english.pickle: (1) its trained collocations (`(typ, next_typ)`
+    pairs that cancel a break) are not available; (2) for an initial or a number followed by a lower-case token whose
+    orthographic context in the training corpus is "sentence-initial lower-case only", Punkt keeps the break and this
+    module does not; (3) `!`/`?` inside a word followed by letters (`wh!mr. x`) count as breaks in Punkt's context
+    tokenization and are ignored here; (4) the non-word character class is the pre-3.6.6 one (with `?`); (5) the
+    abbreviation set is whatever the caller passes (engine.load_words(..., abbrev=...)), not english.pickle's.
 
 The CUDA kernel (leaf_b200/csrc/constrain_core.cuh) is pinned bit-exactly against THIS module; this module is what a
 user with NLTK installed should check first (tools/validate_constrain.py does that and reports the mismatch rate).
@@ -86,52 +95,84 @@ _NUMBER = re.compile(r"^-?[\.,]?\d[\d,\.-]*$")         # punkt.py :: PunktToken.
 _CLOSERS = set("\"')]}")                              # punkt.py :: _re_boundary_realignment
 
 
+def _is_end_context(text: str, i: int) -> bool:
+    """punkt.py :: PunktLanguageVars._period_context_fmt at position i: a sentence-end character followed by a non-word
+    character, or by whitespace and another token."""
+    n = len(text)
+    if text[i] not in ".?!" or i + 1 >= n:
+        return False
+    if text[i + 1] in NONWORD:
+        return True
+    j = i + 1
+    while j < n and text[j] in _WS:
+        j += 1
+    return j > i + 1 and j < n
+
+
 def sent_split(text: str, abbrev=frozenset()) -> list:
-    """Sentence strings of `text` (already lower-cased by the caller, utils_attacks.py:132)."""
+    """Sentence strings of `text` (already lower-cased by the caller, utils_attacks.py:132).
+
+    Potential sentence ends that sit in the SAME whitespace-delimited word (`this!!! that`, `cat.! b`) are one decision, taken
+    at the last of them (punkt.py :: PunktSentenceTokenizer._match_potential_end_contexts, NLTK >= 3.6.6: a match whose
+    preceding-word slice overlaps the next match's is not yielded; the surviving context holds the whole word, so a
+    sentence break found at any of its end characters counts)."""
     n = len(text)
     out, last = [], 0
     i = 0
+    pending = False                                       # a break decided at an earlier end character of this word
     while i < n:
         c = text[i]
-        if c in ".?!" and i + 1 < n:
+        if _is_end_context(text, i):
             nxt = text[i + 1]
             j = i + 1
             while j < n and text[j] in _WS:
                 j += 1
             after_ws = j > i + 1 and j < n                # whitespace, then another token
-            if nxt in NONWORD or after_ws:
-                brk = True
-                if c == ".":
-                    if (i > 0 and text[i - 1] == ".") or nxt == ".":
-                        brk = False                       # ellipsis / multi-character punctuation
-                    else:
-                        s = i
-                        while s > 0 and text[s - 1] not in _WS and text[s - 1] not in NONWORD:
-                            s -= 1
-                        stem = text[s:i]
-                        if stem:
-                            if stem in abbrev or stem.split("-")[-1] in abbrev:
-                                brk = False
-                            elif len(stem) == 1 and stem.isalpha():
-                                brk = False               # an initial followed by lower-case text
-                            elif _NUMBER.match(stem):
-                                brk = False               # a number / ordinal followed by lower-case text
-                if brk:
-                    end = i + 1
-                    start = j if after_ws else i + 1
-                    # realign: closing quotes / brackets that open the next sentence belong to this one
-                    k = start
-                    while k < n and text[k] in _CLOSERS:
+            brk = True
+            if c == ".":
+                if (i > 0 and text[i - 1] == ".") or nxt == ".":
+                    brk = False                       # ellipsis / multi-character punctuation
+                else:
+                    s = i
+                    while s > 0 and text[s - 1] not in _WS and text[s - 1] not in NONWORD:
+                        s -= 1
+                    stem = text[s:i]
+                    if stem:
+                        if stem in abbrev or stem.split("-")[-1] in abbrev:
+                            brk = False
+                        elif len(stem) == 1 and stem.isalpha():
+                            brk = False               # an initial followed by lower-case text
+                        elif _NUMBER.match(stem):
+                            brk = False               # a number / ordinal followed by lower-case text
+            later = False                                 # another potential end further on in the same word?
+            k = i + 1
+            while k < n and text[k] not in _WS:
+                if _is_end_context(text, k):
+                    later = True
+                    break
+                k += 1
+            if later:
+                pending |= brk
+                i += 1
+                continue
+            brk |= pending
+            pending = False
+            if brk:
+                end = i + 1
+                start = j if after_ws else i + 1
+                # realign: closing quotes / brackets that open the next sentence belong to this one
+                k = start
+                while k < n and text[k] in _CLOSERS:
+                    k += 1
+                if k > start and (k == n or text[k] in _WS or text.startswith("--", k)):
+                    end = k
+                    while k < n and text[k] in _WS:
                         k += 1
-                    if k > start and (k == n or text[k] in _WS or text.startswith("--", k)):
-                        end = k
-                        while k < n and text[k] in _WS:
-                            k += 1
-                        start = k
-                    out.append(text[last:end])
-                    last = start
-                    i = max(i + 1, start)
-                    continue
+                    start = k
+                out.append(text[last:end])
+                last = start
+                i = max(i + 1, start)
+                continue
         i += 1
     tail = text[last:].rstrip("".join(_WS))
     out.append(tail)

@@ -319,6 +319,27 @@ def test_constrain_mask_matches_oracle(eng):
     assert flags == 0 and np.array_equal(counts.cpu().numpy(), hc)
 
 
+def test_constrain_kernel_counts_nltk_published_vectors(eng):
+    """leaf_constrain_mask on the word_tokenize vectors NLTK itself publishes (tests/golden/nltk_published_vectors.json): with the
+    published tokens as the dictionary the device count is the number of distinct published tokens, with the glued
+    whitespace forms as the dictionary it is 0 (same check as tests/test_constrain_cpu.py runs on the CPU-compiled core)."""
+    from tests.test_constrain_cpu import published_count_cases
+    cases = published_count_cases()
+    assert len(cases) >= 15
+    pos = torch.zeros((1, 1), dtype=torch.int32, device="cuda")
+    chr_ = torch.full((1, 1), -1, dtype=torch.int32, device="cuda")
+    for text, abbrev, want, glued in cases:
+        d, o = eng.upload_captions([text])
+        eng.load_words(want, abbrev)
+        _, counts = eng.constrain_mask(d, o, 1, 1, pos, chr_, want_counts=True)
+        assert counts.cpu().tolist() == [len(want), len(want)], (text, counts.cpu().tolist(), want)
+        if glued:
+            eng.load_words(glued, abbrev)
+            _, counts = eng.constrain_mask(d, o, 1, 1, pos, chr_, want_counts=True)
+            assert counts.cpu().tolist() == [0, 0], (text, glued)
+    eng.check_status()
+
+
 def test_hf_tokenizer_mode_and_hf_shaped_rows(eng, golden_dir):
     """HF wire compatibility: token ids of transformers' CLIPTokenizer, the tokenizer_wrapper layout
     (padded to the longest row with the pad id), and the forward on such rows with HF's first-EOS pooling."""

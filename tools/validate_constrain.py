@@ -4,7 +4,12 @@ restatement of the reference's `--constrain` filter (oracle/nltk_restate.py, whi
 from NLTK itself - the parity this repo could not pin offline. No GPU needed.
 
     python tools/validate_constrain.py [captions.txt]        # one caption per line; default: built-in samples
+
+It also replays tests/golden/nltk_published_vectors.json (NLTK's own docstring / doctest / unit-test examples, transcribed by
+hand because NLTK is not installable in the build image) through the installed NLTK and reports every transcription error,
+and writes the whole outcome to profiles/constrain_vs_nltk_report.txt so that it can be committed.
 """
+import json
 import os
 import random
 import sys
@@ -33,6 +38,17 @@ rng = random.Random(0)
 V = [-1] + [ord(c) for c in "abcdefghijklmnopqrstuvwxyz ABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789!\"#$%&'()*+,-./:;<=>?@[\\]^_`{|}~"]
 from oracle.leaf_oracle import edit_sentence  # noqa: E402
 
+report = []
+pub = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "nltk_published_vectors.json")))
+from nltk.tokenize import NLTKWordTokenizer, sent_tokenize  # noqa: E402
+wrong = 0
+for v in pub["vectors"]:
+    got = {"treebank": lambda t: NLTKWordTokenizer().tokenize(t), "word_tokenize": word_tokenize, "sent_tokenize": sent_tokenize}[v["kind"]](v["text"])
+    if got != v["expected"]:
+        wrong += 1
+        report.append(f"PUBLISHED VECTOR MISMATCH ({v['source']}): {v['text']!r}\n   nltk {nltk.__version__}: {got}\n   fixture: {v['expected']}")
+report.append(f"published vectors: {len(pub['vectors']) - wrong}/{len(pub['vectors'])} reproduced by nltk {nltk.__version__}")
+
 tot = tok_bad = cnt_bad = 0
 for S in caps:
     for _ in range(200):
@@ -41,6 +57,10 @@ for S in caps:
         tot += 1
         tok_bad += a != b
         cnt_bad += len(W.intersection(a)) != len(W.intersection(b))
-        if a != b and tok_bad <= 10:
-            print("DIFF", repr(s), a, b)
-print(f"{tot} candidates: token lists differ on {tok_bad} ({tok_bad / tot:.2%}), dictionary-word counts on {cnt_bad} ({cnt_bad / tot:.2%})")
+        if a != b and tok_bad <= 50:
+            report.append(f"DIFF {s!r}\n   nltk: {a}\n   restatement: {b}")
+report.append(f"{tot} candidates: token lists differ on {tok_bad} ({tok_bad / tot:.2%}), dictionary-word counts on {cnt_bad} ({cnt_bad / tot:.2%})")
+print("\n".join(report))
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "constrain_vs_nltk_report.txt")
+open(out, "w").write("\n".join(report) + "\n")
+print("written to", out)
