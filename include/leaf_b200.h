@@ -186,6 +186,17 @@ int leaf_forward_train(leaf_handle_t h, const int32_t* tok, const int32_t* len, 
 int leaf_backward(leaf_handle_t h, int64_t generation, const float* dfeat, int32_t dfeat_rows, const leaf_weight_ptrs_t* grads,
                   void* stream);
 
+/* Host callback of leaf_backward, the hook the data-parallel gradient exchange hangs on (what DDP's bucketed all-reduce does
+ * for the reference, train_AT_text_only.py:310-317): called on the calling thread, in stream order, with
+ *   layer == L (the layer count)  after the text_projection / ln_final gradients have been enqueued,
+ *   layer == L-1 ... 0            after ALL weight gradients of that layer have been enqueued (the bias and LayerNorm
+ *                                 gradients of the layers above it are complete at that point as well),
+ *   layer == -1                   at the end (embedding gradients enqueued).
+ * "Enqueued" means: an event recorded on `stream` inside the callback completes after those gradients are final, so a
+ * second stream can all-reduce that slice while the backward of the layers below still runs. fn == NULL removes it. */
+typedef void (*leaf_backward_hook_t)(int32_t layer, void* user);
+int leaf_set_backward_hook(leaf_handle_t h, leaf_backward_hook_t fn, void* user);
+
 /* AdamW (torch.optim.AdamW semantics, decoupled weight decay) over the tower's parameters held in ONE flat fp32 buffer
  * (train_AT_text_only.py:326-341: the gain / bias / LayerNorm group with weight_decay 0 is laid out first, elements
  * [0, n_nodecay); utils_AT.py:358-362). grads are multiplied by grad_scale first (1/accum_freq, or a clipping

@@ -48,6 +48,7 @@ SIGNATURES = {
     "leaf_train_reserve": (c_int, [c_void_p, c_int]),
     "leaf_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, ctypes.POINTER(c_i64), c_void_p]),
     "leaf_backward": (c_int, [c_void_p, c_i64, c_void_p, c_int, ctypes.POINTER(LeafWeightPtrs), c_void_p]),
+    "leaf_set_backward_hook": (c_int, [c_void_p, c_void_p, c_void_p]),
     "leaf_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_float, ctypes.c_float,
                            ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int, ctypes.c_float, c_void_p]),
     "leaf_sumsq": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
@@ -63,6 +64,8 @@ SIGNATURES = {
     "leaf_set_timing": (c_int, [c_void_p, c_int]),
     "leaf_timing_ms": (ctypes.c_double, [c_void_p, c_int, ctypes.POINTER(c_int)]),
 }
+
+BACKWARD_HOOK = ctypes.CFUNCTYPE(None, c_int, c_void_p)      # leaf_backward_hook_t
 
 _lib = None
 

@@ -96,6 +96,8 @@ struct leaf_engine {
   __nv_bfloat16* proj_w = nullptr;    // [E, W] bf16
   TrainWs tw;
   int64_t train_generation = 0;
+  leaf_backward_hook_t bwd_hook = nullptr;   // host callback after each layer's gradients are enqueued (leaf_set_backward_hook)
+  void* bwd_hook_user = nullptr;
   // workspace
   int max_seqs = 0;
   long rows_cap = 0;
@@ -876,6 +878,7 @@ extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* d
   // that dx: ln_final / the layer above's ln_1 for fc2, this layer's ln_2 for out-proj
   if ((rc = launch_layernorm_bwd(e, t.dtmp, t.x_out, t.eos_row, N, e->wp.lnf_w, t.dx, 0, F(grads->lnf_w), F(grads->lnf_b), scratch, st, t.dx16,
                                  F(grads->layers[e->cfg.layers - 1].fc2_b)))) return rc;
+  if (e->bwd_hook) e->bwd_hook(e->cfg.layers, e->bwd_hook_user);          // projection + ln_final gradients are enqueued
   for (int l = e->cfg.layers - 1; l >= 0; --l) {
     const leaf_layer_ptrs_t& p = e->layer_ptrs[l];
     const leaf_layer_ptrs_t& g = grads->layers[l];
@@ -915,6 +918,8 @@ extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* d
     }
     if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_in, nullptr, M, p.ln1_w, t.dx, 1, F(g.ln1_w), F(g.ln1_b), scratch, st, t.dx16,
                                    l > 0 ? F(grads->layers[l - 1].fc2_b) : nullptr))) return rc;
+    // layer l's weight gradients (and every bias / LayerNorm gradient of layers > l) are complete on the stream from here on
+    if (e->bwd_hook) e->bwd_hook(l, e->bwd_hook_user);
   }
   if (grads->token_embedding || grads->positional_embedding) {
     // a frozen table still needs a target for the atomics: reuse dtmp as a sink is not possible (49408 rows) -> require both
@@ -925,6 +930,14 @@ extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* d
   }
   CK(cudaGetLastError());
   t.have_forward = false;                              // consumed: dx / dtmp were overwritten, a second backward would be wrong
+  if (e->bwd_hook) e->bwd_hook(-1, e->bwd_hook_user);  // everything, embeddings included
+  return LEAF_OK;
+}
+
+extern "C" int leaf_set_backward_hook(leaf_handle_t e, leaf_backward_hook_t fn, void* user) {
+  if (!e) return fail(LEAF_ERR_INVALID, "null handle");
+  e->bwd_hook = fn;
+  e->bwd_hook_user = user;
   return LEAF_OK;
 }
 

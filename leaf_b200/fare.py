@@ -11,11 +11,12 @@ from __future__ import annotations
 
 import ctypes
 import math
+import weakref
 
 import torch
 import torch.distributed as dist
 
-from ._native import check
+from ._native import BACKWARD_HOOK, check
 from .attack import V_DEFAULT, attack_text_leaf
 from .engine import _ptr, _stream
 from .eval_attacks import attack_text_charmer_inference
@@ -29,7 +30,7 @@ class FareTrainer:
     def __init__(self, tower: LeafTextTower, frozen: LeafTextTower, V=V_DEFAULT, rho: int = 50, k_adv: int = 1, lr: float = 1e-5,
                  wd: float = 1e-4, beta1: float = 0.9, beta2: float = 0.98, eps: float = 1e-6, accum_freq: int = 1,
                  grad_clip_norm: float = None, constrain=False, normalize_fare: bool = False, use_charmer: bool = False,
-                 group=None):
+                 group=None, overlap_allreduce: bool = True):
         self.tower, self.frozen, self.V = tower, frozen, list(V)
         self.rho, self.k_adv, self.constrain = rho, k_adv, constrain
         self.lr, self.wd, self.beta1, self.beta2, self.eps = lr, wd, beta1, beta2, eps
@@ -43,6 +44,66 @@ class FareTrainer:
         self._norm = torch.zeros(1, dtype=torch.float32, device=tower.flat_params.device)
         self.opt_step = 0            # optimizer steps taken
         self.micro = 0               # micro-batches seen
+        # ---- data-parallel gradient exchange overlapped with the backward (what DDP's bucketed all-reduce does for the
+        #      reference, train_AT_text_only.py:310-317): leaf_backward calls back after every layer; the callback records an
+        #      event and queues an all-reduce of that layer's slice of the flat gradient buffer behind it on a side stream ----
+        self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.overlap_allreduce = bool(overlap_allreduce) and self._distributed
+        self._works, self._reduced = [], False
+        if self.overlap_allreduce:
+            self._side = torch.cuda.Stream(device=tower.flat_params.device)
+            self._layer_ranges, self._rest_ranges = self._gradient_ranges()
+            self._hook_armed = False
+            me = weakref.ref(self)
+
+            def thunk(layer, user):                           # a no-op once this trainer is gone (the engine may outlive it)
+                tr = me()
+                if tr is not None:
+                    tr._on_backward_layer(layer, user)
+
+            eng = tower.leaf_engine
+            eng._backward_hook = BACKWARD_HOOK(thunk)         # the ctypes thunk lives as long as the engine that calls it
+            check(eng._lib.leaf_set_backward_hook(eng._h, ctypes.cast(eng._backward_hook, ctypes.c_void_p), None))
+
+    def _gradient_ranges(self):
+        """Contiguous [lo, hi) element ranges of the flat gradient buffer: one list per layer holding that layer's weight
+        MATRICES (adjacent in the buffer: the stable sort of LeafTextTower keeps the state dict's layer order inside the
+        weight-decay group), and the rest (every 1-D parameter, the embeddings, the projection) reduced at the end."""
+        t = self.tower
+        span = lambda k: (t._slices[k][0], t._slices[k][0] + (t._slices[k][1] + 3) // 4 * 4)
+        per_layer, taken = [], []
+        for l in range(t.leaf_engine.layers):
+            ks = [k for k in t._slices if k.startswith(f"transformer.resblocks.{l}.") and len(t._slices[k][2]) >= 2]
+            per_layer.append(self._merge([span(k) for k in ks]))
+            taken += ks
+        rest = self._merge([span(k) for k in t._slices if k not in taken])
+        return per_layer, rest
+
+    @staticmethod
+    def _merge(spans):
+        out = []
+        for lo, hi in sorted(spans):
+            if out and out[-1][1] == lo:
+                out[-1][1] = hi
+            else:
+                out.append([lo, hi])
+        return [tuple(x) for x in out]
+
+    def _on_backward_layer(self, layer, _user):
+        if not self._hook_armed:
+            return
+        ranges = self._rest_ranges if layer == -1 else self._layer_ranges[layer] if layer < len(self._layer_ranges) else []
+        if not ranges:
+            return
+        g = self.tower.flat_grads
+        ev = torch.cuda.Event()
+        ev.record()                                           # after this layer's gradients on the backward's stream
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            for lo, hi in ranges:
+                self._works.append(dist.all_reduce(g[lo:hi], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        if layer == -1:
+            self._reduced = True
 
     # ---- pieces (public so that a caller can keep its own loop and swap single stages) -------------------------------
     @torch.no_grad()
@@ -69,8 +130,13 @@ class FareTrainer:
         engine re-casts its bf16 operand copies from the updated fp32 parameters."""
         t = self.tower
         g, eng = t.flat_grads, t.leaf_engine
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+        if self._distributed:
+            if self._reduced:                                 # already exchanged slice by slice while the backward ran
+                for w in self._works:
+                    w.wait()                                  # stream-level: the optimizer kernels queue behind the collectives
+                self._works, self._reduced = [], False
+            else:
+                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
         scale = grad_scale
         if self.grad_clip_norm is not None:                       # torch.nn.utils.clip_grad_norm_, norm_type 2
             self._norm.zero_()
@@ -94,7 +160,11 @@ class FareTrainer:
         tok = t.tokenizer(adv_texts)                                                       # :312
         feats = t.encode_text(tok, normalize=self.normalize_fare)                          # :317-319 (train mode == eval: no dropout)
         loss = torch.nn.functional.mse_loss(anchors, feats, reduction="none").sum(dim=-1).mean()      # :321-322
+        if self.overlap_allreduce:                           # exchange during the LAST micro-batch's backward only (DDP no_sync)
+            self._hook_armed = (self.micro + 1) % self.accum_freq == 0
         (loss / self.accum_freq).backward()                                                # :329-337
+        if self.overlap_allreduce:
+            self._hook_armed = False
         self.micro += 1
         if self.micro % self.accum_freq == 0:
             self.optimizer_step()

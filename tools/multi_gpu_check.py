@@ -40,17 +40,31 @@ for mode in ("samples", "candidates"):
     close = torch.equal(res[mode][0], res[None][0])
     print(f"rank {rank}: shard={mode}: winners equal {same}, features bit-equal {close}", flush=True)
     ok &= same and close
-# data-parallel FARE step: each rank its own micro-batch, gradients averaged by ONE all-reduce of the flat buffer;
-# afterwards the parameters must be identical on every rank
-tr = FareTrainer(tower, frozen, rho=20, k_adv=1, lr=1e-4)
-np.random.seed(100 + rank)
-loss, _ = tr.step(synth.make_captions(8, seed=50 + rank))
-flat = tower.flat_params.clone()
-ref = flat.clone()
-dist.broadcast(ref, src=0)
-same_params = torch.equal(flat, ref)
-print(f"rank {rank}: FARE step loss {loss.item():.4f}, parameters identical across ranks after the update: {same_params}", flush=True)
-ok &= same_params
+# data-parallel FARE step: each rank its own micro-batch. Gradients are averaged (a) by ONE blocking all-reduce of the flat
+# buffer after the backward, (b) slice by slice on a side stream WHILE the backward runs (leaf_set_backward_hook). Both must
+# leave identical parameters on every rank, and (a) and (b) must agree (same sums, possibly another order inside NCCL).
+state0 = tower.flat_params.clone()
+outs = {}
+for overlap in (False, True):
+    tower.flat_params.copy_(state0)
+    tower.refresh()
+    tr = FareTrainer(tower, frozen, rho=20, k_adv=1, lr=1e-4, accum_freq=2, overlap_allreduce=overlap)
+    for mb in range(2):                                  # two micro-batches, one optimizer step
+        np.random.seed(100 + rank + 10 * mb)
+        loss, _ = tr.step(synth.make_captions(8, seed=50 + rank + 10 * mb))
+    flat = tower.flat_params.clone()
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    same_params = torch.equal(flat, ref)
+    outs[overlap] = flat
+    print(f"rank {rank}: FARE step (overlap_allreduce={overlap}) loss {loss.item():.4f}, optimizer steps {tr.opt_step}, parameters identical "
+          f"across ranks after the update: {same_params}, moved: {not torch.equal(flat, state0)}", flush=True)
+    ok &= same_params and tr.opt_step == 1 and not torch.equal(flat, state0)
+    del tr
+diff = (outs[True] - outs[False]).abs().max().item()
+upd = (outs[False] - state0).abs().max().item()
+print(f"rank {rank}: overlapped vs blocking exchange: max |difference| of the updated parameters {diff:.3e} (update size {upd:.3e})", flush=True)
+ok &= diff <= 1e-2 * upd + 1e-12
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
