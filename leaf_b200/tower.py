@@ -62,6 +62,53 @@ def text_tower_state_dict(state_dict: dict) -> dict:
     return out
 
 
+def open_clip_to_hf(sd: dict) -> dict:
+    """The reference's export mapping (conversion/convert_2.py:37-99, copy_text_model_and_projection): an open_clip text-tower
+    state dict -> the keys of transformers' CLIPTextModelWithProjection (equally the text half of a CLIPModel): fused
+    in_proj split into q / k / v (`chunk(3, dim=0)`, :39-40), c_fc / c_proj -> fc1 / fc2, ln_1 / ln_2 -> layer_norm1 / 2,
+    positional_embedding -> position_embedding.weight, text_projection [W,E] -> text_projection.weight = P^T [E,W] (:85).
+    Tensors are new (contiguous copies), on the source's device."""
+    sd = text_tower_state_dict(sd)
+    out = {"text_model.embeddings.token_embedding.weight": sd["token_embedding.weight"].clone(),
+           "text_model.embeddings.position_embedding.weight": sd["positional_embedding"].clone(),
+           "text_model.final_layer_norm.weight": sd["ln_final.weight"].clone(),
+           "text_model.final_layer_norm.bias": sd["ln_final.bias"].clone(),
+           "text_projection.weight": sd["text_projection"].t().contiguous()}
+    i = 0
+    while f"transformer.resblocks.{i}.ln_1.weight" in sd:
+        p, q = f"transformer.resblocks.{i}.", f"text_model.encoder.layers.{i}."
+        for nm, w, b in zip("qkv", sd[p + "attn.in_proj_weight"].chunk(3, dim=0), sd[p + "attn.in_proj_bias"].chunk(3, dim=0)):
+            out[q + f"self_attn.{nm}_proj.weight"], out[q + f"self_attn.{nm}_proj.bias"] = w.contiguous().clone(), b.contiguous().clone()
+        for a, b in (("attn.out_proj", "self_attn.out_proj"), ("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"),
+                     ("mlp.c_fc", "mlp.fc1"), ("mlp.c_proj", "mlp.fc2")):
+            out[q + b + ".weight"], out[q + b + ".bias"] = sd[p + a + ".weight"].clone(), sd[p + a + ".bias"].clone()
+        i += 1
+    return out
+
+
+def hf_to_open_clip(sd: dict) -> dict:
+    """The inverse mapping (the direction of the reference's convert_to_openclip.py): HF CLIPTextModel(WithProjection) /
+    CLIPModel keys -> an open_clip text-tower state dict LeafTextTower accepts."""
+    pre = next((k[: -len("embeddings.token_embedding.weight")] for k in sd if k.endswith("embeddings.token_embedding.weight")), None)
+    if pre is None:
+        raise ValueError("not an HF CLIP text state dict (no embeddings.token_embedding.weight)")
+    root = pre[: -len("text_model.")] if pre.endswith("text_model.") else pre
+    out = {"token_embedding.weight": sd[pre + "embeddings.token_embedding.weight"].clone(),
+           "positional_embedding": sd[pre + "embeddings.position_embedding.weight"].clone(),
+           "ln_final.weight": sd[pre + "final_layer_norm.weight"].clone(), "ln_final.bias": sd[pre + "final_layer_norm.bias"].clone(),
+           "text_projection": sd[root + "text_projection.weight"].t().contiguous()}
+    i = 0
+    while (pre + f"encoder.layers.{i}.layer_norm1.weight") in sd:
+        q, p = pre + f"encoder.layers.{i}.", f"transformer.resblocks.{i}."
+        out[p + "attn.in_proj_weight"] = torch.cat([sd[q + f"self_attn.{nm}_proj.weight"] for nm in "qkv"], dim=0)
+        out[p + "attn.in_proj_bias"] = torch.cat([sd[q + f"self_attn.{nm}_proj.bias"] for nm in "qkv"], dim=0)
+        for a, b in (("attn.out_proj", "self_attn.out_proj"), ("ln_1", "layer_norm1"), ("ln_2", "layer_norm2"),
+                     ("mlp.c_fc", "mlp.fc1"), ("mlp.c_proj", "mlp.fc2")):
+            out[p + a + ".weight"], out[p + a + ".bias"] = sd[q + b + ".weight"].clone(), sd[q + b + ".bias"].clone()
+        i += 1
+    return out
+
+
 class LeafTextTower(torch.nn.Module):
     _leaf_self_managed = True            # engine.bind_module: this module refreshes its own engine (refresh())
 
@@ -96,6 +143,43 @@ class LeafTextTower(torch.nn.Module):
         cfg = synth.TOWERS[name_or_cfg] if isinstance(name_or_cfg, str) else name_or_cfg
         sd = synth.random_tower_state_dict(cfg, seed=seed, device="cpu" if exact_numpy else device, exact_numpy=exact_numpy)
         return cls(sd, heads=cfg.heads, quick_gelu=cfg.quick_gelu, device=device)
+
+    @classmethod
+    def from_hf(cls, hf_model, device="cuda"):
+        """A trainable LeafTextTower from a transformers CLIPTextModelWithProjection / CLIPModel (weights COPIED into the flat
+        buffer; export back with hf_state_dict / load_into_hf)."""
+        cfg = getattr(hf_model.config, "text_config", None) or hf_model.config
+        if cfg.hidden_act not in ("gelu", "quick_gelu"):
+            raise ValueError(f"unsupported activation {cfg.hidden_act!r}")
+        sd = hf_to_open_clip({k: v.detach() for k, v in hf_model.state_dict().items()})
+        return cls(sd, heads=int(cfg.num_attention_heads), quick_gelu=cfg.hidden_act == "quick_gelu", device=device)
+
+    def hf_state_dict(self) -> dict:
+        """The tower's CURRENT parameters under transformers' CLIPTextModelWithProjection keys - the reference's HF
+        checkpoint export (conversion/convert_2.py:37-99) for a tower trained here."""
+        return open_clip_to_hf(self.open_clip_state_dict())
+
+    def hf_text_config(self, **overrides):
+        """transformers.CLIPTextConfig of this tower (what conversion/convert_2.py builds from the open_clip config)."""
+        from transformers import CLIPTextConfig
+        e = self.leaf_engine
+        kw = dict(vocab_size=int(self._slices["token_embedding.weight"][2][0]), hidden_size=e.width, intermediate_size=4 * e.width,
+                  num_hidden_layers=e.layers, num_attention_heads=e.heads, max_position_embeddings=int(self._slices["positional_embedding"][2][0]),
+                  hidden_act="quick_gelu" if self.quick_gelu else "gelu", projection_dim=e.embed_dim, layer_norm_eps=1e-5,
+                  bos_token_id=49406, eos_token_id=49407, pad_token_id=49407)
+        kw.update(overrides)
+        return CLIPTextConfig(**kw)
+
+    def load_into_hf(self, hf_model=None):
+        """Copy the parameters into `hf_model` (a CLIPTextModelWithProjection, or the text half of a CLIPModel:
+        strict=False leaves its vision tower alone); with None a fresh CLIPTextModelWithProjection is built."""
+        if hf_model is None:
+            from transformers import CLIPTextModelWithProjection
+            hf_model = CLIPTextModelWithProjection(self.hf_text_config())
+        missing, unexpected = hf_model.load_state_dict(self.hf_state_dict(), strict=False)
+        if unexpected or any("text_model" in k or k.startswith("text_projection") for k in missing):
+            raise ValueError(f"HF export does not fit the target model: missing {missing}, unexpected {unexpected}")
+        return hf_model
 
     # ---- parameters ------------------------------------------------------------------------------------------
     def named_tower_parameters(self):

@@ -298,3 +298,33 @@ def test_vit_h_24_layers_tower_and_attack_vs_fp32_oracle():
         assert int(nontied.sum()) >= B // 4 and agree >= 0.99, stats
         sel = want_loss.argmax(-1).to(torch.int32)                                   # phase 2 on the ORACLE's positions: same candidate sets
     print("ViT-H full-size parity (phase, cos_min, loss_rel_max, non-tied, agreement):", stats)
+
+
+def test_hf_import_train_export_round_trip():
+    """HF checkpoint -> LeafTextTower.from_hf -> one FARE update on the engine -> load_into_hf: the exported HF model's own
+    forward reproduces the updated tower (conversion/convert_2.py:37-99 is the mapping; its check is atol 1e-4 between fp32
+    models - here one side computes in bf16, hence the cosine bar)."""
+    from transformers import CLIPTextModelWithProjection
+    from leaf_b200 import synth
+    from leaf_b200.fare import FareTrainer
+    from leaf_b200.tower import LeafTextTower
+    hf = _randomize(CLIPTextModelWithProjection(_hf_text_config(True)), seed=3).eval().cuda()
+    tower = LeafTextTower.from_hf(hf)
+    frozen = LeafTextTower.from_hf(hf)
+    caps = synth.make_captions(8, seed=4)
+    tok = tower.tokenizer(caps)
+    with torch.no_grad():
+        want = hf(tok).text_embeds
+    assert _cos(tower.encode_text(tok), want).min() >= COS_MIN
+    before = tower.flat_params.clone()
+    tr = FareTrainer(tower, frozen, rho=8, k_adv=1, lr=1e-3)
+    np.random.seed(0)
+    tr.step(caps)
+    assert not torch.equal(before, tower.flat_params)
+    hf2 = tower.load_into_hf().cuda().eval()
+    with torch.no_grad():
+        got = hf2(tok).text_embeds
+        assert _cos(tower.encode_text(tok), got).min() >= COS_MIN
+        assert _cos(got, want).min() < 0.99999                                         # the update is in the export
+    sd_hf = tower.hf_state_dict()
+    assert torch.equal(sd_hf["text_model.encoder.layers.0.mlp.fc1.weight"], tower.open_clip_state_dict()["transformer.resblocks.0.mlp.c_fc.weight"])
