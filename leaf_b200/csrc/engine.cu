@@ -21,6 +21,7 @@
 #include "constrain_kernel.cuh"
 #include "k1_tokenize.cuh"
 #include "tower_kernels.cuh"
+#include "attention2.cuh"
 #include "train_kernels.cuh"
 
 using namespace leaf;
@@ -109,6 +110,7 @@ struct leaf_engine {
   float* xc = nullptr;                // [max_seqs, W] fp32 residual rows of the pooled positions (final layer, compact)
   int* first_of = nullptr;            // [max_seqs] sequence whose rows stand for sequence i
   bool prune_last = true;             // final layer: out-proj + MLP on the pooled rows only
+  int att_impl = 1;                   // 1 = register-fed attention_kernel (default: faster in situ), 2 = cp.async ring attention2_kernel (LEAF_ATTENTION_IMPL=2)
   int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr, *dup_of = nullptr, *need = nullptr;
   int4* meta = nullptr;
   // bookkeeping
@@ -268,6 +270,9 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  if (const char* ai = getenv("LEAF_ATTENTION_IMPL")) e->att_impl = atoi(ai) == 2 ? 2 : 1;
   CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attb_smem_bytes(LEAF_CTX)));
   *out = e;
   return LEAF_OK;
@@ -489,8 +494,17 @@ static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev,
 
 // causal attention over the packed rows (tower_kernels.cuh)
 static int launch_attention(leaf_engine* e, const __nv_bfloat16* qkv, const int4* meta, int N, __nv_bfloat16* out, int last_only,
-                            cudaStream_t st) {
+                            cudaStream_t st, long rows_cap_hint = 0) {
+  if (rows_cap_hint <= 0) rows_cap_hint = static_cast<long>(N) * LEAF_CTX;      // no sequence has more than 77 rows
   const int H = e->cfg.heads, W = e->cfg.width;
+  if (e->att_impl == 2 && static_cast<unsigned long long>(rows_cap_hint) * 3ull * W < (1ull << 32)) {
+    const long ctas = (static_cast<long>(N) * H + AT2_WARPS - 1) / AT2_WARPS;
+    const int grid2 = static_cast<int>(ctas < 2L * e->sm_count ? ctas : 2L * e->sm_count);     // persistent: 2 CTAs of 8 warps per SM
+    attention2_kernel<<<grid2, AT2_WARPS * 32, AT2_SMEM_BYTES, st>>>(qkv, meta, N, H, W, out, last_only);
+    e->launches++;
+    CK(cudaGetLastError());
+    return LEAF_OK;
+  }
   const int grid = (N * H + ATT_WARPS - 1) / ATT_WARPS;
   attention_kernel<<<grid, ATT_WARPS * 32, 0, st>>>(qkv, meta, N, H, W, out, last_only);
   e->launches++;

@@ -99,6 +99,7 @@ class LeafEngine:
         self.width = int(c["tok"].shape[1])
         self.layers = len(c["layers"])
         self.heads = int(heads)
+        self.quick_gelu, self.ln_eps = bool(quick_gelu), float(ln_eps)
         self.embed_dim = int(c["proj"].shape[0] if c["proj_is_ew"] else c["proj"].shape[1])
         self.device = c["tok"].device
         self._check_tensors()

@@ -49,7 +49,7 @@ def main():
     H, W = 16, 1024
     cfg = synth.TowerCfg("ab", W, 1, H, 1024)               # the kernel only depends on heads and width
     for v in variants:
-        os.environ["LEAF_ATT_VARIANT"] = str(v)
+        os.environ["LEAF_ATTENTION_IMPL"] = str(v)
         engines[v] = LeafTextTower.random(cfg, seed=0, device=dev).leaf_engine
     eng = engines[variants[0]]
     assert eng.width == W and eng.heads == H, (eng.width, eng.heads)
