@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train-step", action="store_true", help="skip the full FARE step (attack + K4 + AdamW) leg")
+    ap.add_argument("--no-overlap-allreduce", action="store_true", help="FARE step: one blocking all-reduce after the backward instead of the per-layer overlapped exchange")
     ap.add_argument("--no-library-baseline", action="store_true", help="skip the stock-PyTorch-on-the-same-GPU leg (N = 1 only)")
     ap.add_argument("--no-dense77", action="store_true", help="skip the worst-case (every row truncated to 77 tokens) leg")
     ap.add_argument("--no-global-batch", action="store_true", help="skip the strong-scaling legs with a collective on the path (N > 1 only)")
@@ -371,7 +372,8 @@ def run_ours(a):
         from leaf_b200.fare import FareTrainer
         frozen2 = LeafTextTower(synth.perturbed_copy(tower.open_clip_state_dict(), seed=1, std=1e-3), heads=cfg.heads,
                                 quick_gelu=cfg.quick_gelu, device=dev)
-        trainer = FareTrainer(tower, frozen2, rho=n, k_adv=k, lr=1e-5, wd=1e-4, beta1=0.9, beta2=0.98, eps=1e-6)   # scripts/train_leaf_vith.sh
+        trainer = FareTrainer(tower, frozen2, rho=n, k_adv=k, lr=1e-5, wd=1e-4, beta1=0.9, beta2=0.98, eps=1e-6,   # scripts/train_leaf_vith.sh
+                              overlap_allreduce=not a.no_overlap_allreduce)
 
         def train_step(seed):
             np.random.seed(seed)
@@ -390,7 +392,7 @@ def run_ours(a):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         train = dict(ms_per_step=tt.item(), attack_ms_per_step=e2e_ms / a.steps, loss_first=losses[0], loss_last=losses[-1],
                      what="leaf_b200.fare.FareTrainer.step: frozen anchors + attack_text_leaf + tokenize winners + forward/backward "
-                          "(K4, gradients accumulated into one flat buffer) + " + ("NCCL all-reduce + " if world > 1 else "")
+                          "(K4, gradients accumulated into one flat buffer) + " + (("NCCL all-reduce (" + ("one blocking call after the backward" if a.no_overlap_allreduce else "per-layer slices on a side stream while the backward runs") + ") + ") if world > 1 else "")
                           + "native AdamW (one launch) + weight refresh")
         tower.trainable(False)
         del trainer, frozen2

@@ -192,7 +192,8 @@ struct TimedSpan {
 // C[M,N] = A[M,K] . Bt[N,K]^T with the fused epilogue `epi`
 static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, const __nv_bfloat16* Bt, const float* bias,
                        void* C, int ldc, int M, int N, int K, int epi, int act, const int* m_dev, cudaStream_t st,
-                       const __nv_bfloat16* delta = nullptr, int mn_major = 0, long a_pitch = 0, const float* res = nullptr) {
+                       const __nv_bfloat16* delta = nullptr, int mn_major = 0, long a_pitch = 0, const float* res = nullptr,
+                       void* C2 = nullptr, bool allow_split_k = false) {
   if (M <= 0 || N <= 0 || K <= 0) return fail(LEAF_ERR_INVALID, "GEMM shape %dx%dx%d", M, N, K);
   if (N % 8 != 0) return fail(LEAF_ERR_INVALID, "GEMM N (%d) must be a multiple of 8", N);
   CUtensorMap ta, tb;
@@ -211,13 +212,30 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   GemmParams p;
   p.mn_major = mn_major;
   p.res = res;
+  p.C2 = C2;
+  p.split_k = 1;
   p.tx_bytes = static_cast<uint32_t>(a_box + b_box) * GEMM_BK * 2 * 2;       // both CTAs of the pair
   p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act; p.delta = delta;
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
-  const long tiles = static_cast<long>(m_tiles) * n_tiles;
-  TimedSpan span(e, (epi == EPI_F32_RESIDUAL && K > N) ? 8 : (epi == EPI_BF16 && K == N) ? 9 : 4 + epi, st);
-  const int pairs_max = e->sm_count / 2;
-  const int pairs = static_cast<int>(tiles < pairs_max ? tiles : pairs_max);
+  long tiles = static_cast<long>(m_tiles) * n_tiles;
+  const int pairs_cap = e->sm_count / 2;
+  if (allow_split_k && epi == EPI_F32_RESIDUAL && !bias && !delta && !res && !m_dev && tiles < pairs_cap) {
+    // C += A.B with few output tiles and a long contraction (the weight gradients: 16-64 tiles, K = packed rows): divide the
+    // k-blocks over several work units so that the launch fills the 74 CTA pairs; cost model = waves x (k-blocks per part +
+    // 3 for the epilogue and the pipeline ramp). Partial sums are added with red.global.add.v4.f32.
+    const int kblocks = (K + GEMM_BK - 1) / GEMM_BK;
+    long best = ((tiles + pairs_cap - 1) / pairs_cap) * (kblocks + 3);
+    for (int s = 2; s <= 8 && s <= kblocks; ++s) {
+      const int kpb = (kblocks + s - 1) / s;
+      const int s_eff = (kblocks + kpb - 1) / kpb;              // every part non-empty
+      const long cost = ((tiles * s_eff + pairs_cap - 1) / pairs_cap) * (kpb + 3);
+      if (cost < best) { best = cost; p.split_k = s_eff; }
+    }
+    tiles *= p.split_k;
+    if (p.split_k > 1) epi = EPI_F32_SPLITK;
+  }
+  TimedSpan span(e, (epi == EPI_F32_SPLITK) ? 4 + EPI_F32_RESIDUAL : (epi == EPI_F32_RESIDUAL && K > N) ? 8 : (epi == EPI_BF16 && K == N) ? 9 : 4 + epi, st);
+  const int pairs = static_cast<int>(tiles < pairs_cap ? tiles : pairs_cap);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -233,6 +251,7 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
     case EPI_BF16_ACT: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_BF16_ACT>, ta, tb, p)); break;
     case EPI_F32_RESIDUAL: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, ta, tb, p)); break;
     case EPI_F32: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32>, ta, tb, p)); break;
+    case EPI_F32_SPLITK: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32_SPLITK>, ta, tb, p)); break;
     default: return fail(LEAF_ERR_INVALID, "unknown epilogue %d", epi);
   }
   e->launches++;
@@ -269,6 +288,7 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_BF16_ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_SPLITK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -810,10 +830,9 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
     if ((rc = launch_attention(e, a.qkv, t.meta, N, a.o, 0, st))) return rc;
     if ((rc = launch_gemm(e, a.o, t.rows_cap, w.out_w, p.out_b, a.x_mid, W, M, W, W, EPI_F32_RESIDUAL, 0, nullptr, st, nullptr, 0, 0, a.x_in))) return rc;
     if ((rc = launch_layernorm(e, a.x_mid, nullptr, M, nullptr, p.ln2_w, p.ln2_b, a.h2, st))) return rc;
-    if ((rc = launch_gemm(e, a.h2, t.rows_cap, w.fc1_w, p.fc1_b, a.u, 4 * W, M, 4 * W, W, EPI_BF16, 0, nullptr, st))) return rc;
-    const size_t nu = static_cast<size_t>(M) * 4 * W;
-    act_fwd_kernel<<<launch_ew(e, nu), 256, 0, st>>>(a.u, a.g, nu, e->cfg.activation);
-    e->launches++;
+    // one epilogue stores fc1's output twice: the pre-activation u (kept for act'(u) in the backward) and act(u)
+    if ((rc = launch_gemm(e, a.h2, t.rows_cap, w.fc1_w, p.fc1_b, a.g, 4 * W, M, 4 * W, W, EPI_BF16_ACT, e->cfg.activation, nullptr, st,
+                          nullptr, 0, 0, nullptr, a.u))) return rc;
     if ((rc = launch_gemm(e, a.g, t.rows_cap, w.fc2_w, p.fc2_b, x_next, W, M, W, 4 * W, EPI_F32_RESIDUAL, 0, nullptr, st, nullptr, 0, 0, a.x_mid))) return rc;
   }
   if ((rc = launch_layernorm(e, t.x_out, nullptr, N, t.eos_row, e->wp.lnf_w, e->wp.lnf_b, t.pooled, st))) return rc;
@@ -871,7 +890,7 @@ extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* d
   };
   auto wgrad = [&](const __nv_bfloat16* dy, long dy_pitch, const __nv_bfloat16* x, float* dw, int rows, int in, int out) {
     return launch_gemm(e, dy, rows, x, nullptr, dw, in, out, in, rows, EPI_F32_RESIDUAL, 0, nullptr, st, nullptr,
-                       GEMM_A_MN | GEMM_B_MN, dy_pitch);
+                       GEMM_A_MN | GEMM_B_MN, dy_pitch, nullptr, nullptr, /*allow_split_k=*/true);
   };
   // ---- projection + ln_final on the pooled rows ----
   const size_t nfe = static_cast<size_t>(N) * E;
@@ -902,8 +921,8 @@ extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* d
     if ((rc = dgrad(t.dx16, cap, w.fc2_w, t.dtmp, M, 4 * W, W))) return rc;                                 // dg [M,4W]
     if (g.fc2_w && (rc = wgrad(t.dx16, 0, a.g, F(g.fc2_w), M, 4 * W, W))) return rc;
     {
-      const int cb = (4 * W + 255) / 256;
-      int bands = (e->sm_count * 4 + cb - 1) / cb;
+      const int cb = (4 * W + 1023) / 1024;                  // 256 threads x 4 columns
+      int bands = (e->sm_count * 8 + cb - 1) / cb;
       if (bands > M) bands = M;
       act_bwd_kernel<<<dim3(cb, bands), 256, 0, st>>>(t.dtmp, a.u, t.d16, M, 4 * W, e->cfg.activation, F(g.fc1_b));   // du [M,4W] bf16 (+ fc1 bias grad)
       e->launches++;

@@ -102,7 +102,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM;
   const int n_tiles = (p.N + GEMM_BN - 1) / GEMM_BN;
   const int k_blocks = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int total_tiles = m_tiles * n_tiles;
+  // split-K: the k-blocks of an output tile are divided over `split` consecutive work units (GemmParams::split_k)
+  const int split = (EPI == EPI_F32_SPLITK && p.split_k > 1) ? p.split_k : 1;
+  const int kpb = (k_blocks + split - 1) / split;
+  const int total_tiles = m_tiles * n_tiles * split;
 
   if (warp == WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -136,9 +139,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     uint32_t phase = 0;
     const int a_row_off = static_cast<int>(rank) * 128;
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int mn = tile / split, kb0 = (tile - mn * split) * kpb, kb1 = min(k_blocks, kb0 + kpb);
+      const int m_blk = mn / n_tiles, n_blk = mn - m_blk * n_tiles;
       const int a_row = m_blk * GEMM2_BM + a_row_off, b_row = n_blk * GEMM_BN + a_row_off;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         if (elect_one()) {
           const uint32_t sa = smem_base + stage * GEMM2_STAGE_BYTES;
@@ -179,18 +183,19 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * GEMM_BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = (tile % split) * kpb, kb1 = min(k_blocks, kb0 + kpb);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           if (elect_one()) {
             const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (GEMM2_STAGE_BYTES >> 4));
             const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (GEMM2_STAGE_BYTES >> 4));
-            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
+            umma_bf16_2sm(d_tmem, adesc, bdesc, idesc, kb != kb0 ? 1u : 0u);
             umma_bf16_2sm(d_tmem, adesc + ak, bdesc + bk, idesc, 1u);
             umma_bf16_2sm(d_tmem, adesc + 2 * ak, bdesc + 2 * bk, idesc, 1u);
             umma_bf16_2sm(d_tmem, adesc + 3 * ak, bdesc + 3 * bk, idesc, 1u);
             umma_commit_2sm(empty_bar(stage));
-            if (kb == k_blocks - 1) umma_commit_2sm(tfull_bar(acc));
+            if (kb == kb1 - 1) umma_commit_2sm(tfull_bar(acc));
           }
           __syncwarp();
           if (++stage == GEMM2_STAGES) { stage = 0; phase ^= 1; }
@@ -206,7 +211,8 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < total_tiles; tile += n_pairs) {
-      const int m_blk = tile / n_tiles, n_blk = tile % n_tiles;
+      const int mn = tile / split;
+      const int m_blk = mn / n_tiles, n_blk = mn % n_tiles;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int row0 = m_blk * GEMM2_BM + static_cast<int>(rank) * 128 + quad * 32;

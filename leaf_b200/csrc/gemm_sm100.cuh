@@ -29,7 +29,7 @@ constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_UMMA_K = 16;
 
-enum { EPI_BF16 = 0, EPI_BF16_ACT = 1, EPI_F32_RESIDUAL = 2, EPI_F32 = 3 };
+enum { EPI_BF16 = 0, EPI_BF16_ACT = 1, EPI_F32_RESIDUAL = 2, EPI_F32 = 3, EPI_F32_SPLITK = 4 };   // 4: C += partial sums (red.global.add)
 enum { ACT_GELU_ERF = 0, ACT_QUICK_GELU = 1 };
 
 struct GemmParams {
@@ -48,6 +48,14 @@ struct GemmParams {
   // K-major [M, K] / [N, K]. The wgrad product dW[out,in] = dY[rows,out]^T . X[rows,in] reads dY and X as they lie (3), the
   // dgrad product dX[rows,in] = dY[rows,out] . W[out,in] reads the forward's weight copy as it lies (2): no transposes.
   int mn_major;
+  // EPI_BF16_ACT only, may be null: the PRE-activation (acc + bias) is stored here as bf16 as well, same shape as C. The
+  // training forward keeps fc1's output for the backward (act'(u)), so one epilogue writes u and act(u): no separate
+  // activation pass over [rows, 4W] (utils_AT.py:317-319 forward of the winners).
+  void* C2;
+  // split-K (EPI_F32_SPLITK only, no bias): the k-blocks of one output tile are divided over `split_k` work units whose
+  // epilogues ADD their partial sums into C with red.global.add.v4.f32 (C += A.B is what the weight-gradient products want
+  // anyway). Its own template instance, so the hot fc2 epilogue (EPI_F32_RESIDUAL) keeps its register budget. 1 = off.
+  int split_k;
 };
 constexpr int GEMM_A_MN = 1, GEMM_B_MN = 2;
 // MN-major 128B-swizzled tile as TMA lays it down from a [K, MN] row-major tensor with a 64 (MN) x 64 (k) box: one 128-byte
@@ -229,17 +237,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       }
     }
   }
-  if (EPI == EPI_BF16_ACT) {
-    if (p.act == ACT_QUICK_GELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-    }
-  }
   const int c = lane & 3;
-  if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
+  // bf16 tile store: 32 rows x 32 columns through the padded staging buffer, 8 rows x 64 B per store instruction
+  auto store_bf16 = [&](void* dst) {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       uint4 pk;
@@ -260,9 +260,22 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       const int r = it * 8 + (lane >> 2);
       const uint4 pk = *reinterpret_cast<const uint4*>(stage + r * 80 + c * 16);
       if (col_ok && row0 + r < M)
-        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<size_t>(row0 + r) * p.ldc + col0 + c * 8) = pk;
+        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dst) + static_cast<size_t>(row0 + r) * p.ldc + col0 + c * 8) = pk;
     }
-    __syncwarp();                                 // the staging buffer is reused by the next chunk
+    __syncwarp();                                 // the staging buffer is reused by the next store / chunk
+  };
+  if (EPI == EPI_BF16_ACT) {
+    if (p.C2) store_bf16(p.C2);                   // the pre-activation, kept for the backward
+    if (p.act == ACT_QUICK_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = quick_gelu(f[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    }
+  }
+  if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
+    store_bf16(p.C);
   } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -287,7 +300,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       for (int it = 0; it < 4; ++it) {
         const int r = it * 8 + (lane >> 2);
         float4 o = *reinterpret_cast<const float4*>(stage + r * 80 + c * 16);
-        if (col < p.N && row0 + r < M) {
+        if (EPI == EPI_F32_SPLITK) {                        // partial sum of a split-K part: C += o, no read-modify-write
+          if (col < p.N && row0 + r < M)
+            atomicAdd(reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + static_cast<size_t>(row0 + r) * p.ldc + col), o);
+        } else if (col < p.N && row0 + r < M) {
           if (EPI == EPI_F32_RESIDUAL) {
             float4 x = res.x[h * 4 + it];
             if (p.delta) {                              // x + delta first: the sum LayerNorm saw (leaf_encode)

@@ -36,33 +36,37 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat1
 // colsum[c] += sum_r du[r,c], the gradient of fc1's bias. A thread owns one column of a row band (coalesced across the CTA).
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dg, const __nv_bfloat16* __restrict__ u,
                                                       __nv_bfloat16* __restrict__ du, int R, int C, int act, float* __restrict__ colsum) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;     // four adjacent columns per thread: 16-byte dg loads, 8-byte u / du
   if (c >= C) return;
   const int band = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * band, r1 = min(r0 + band, R);
-  float s = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  auto one = [&](const float4 d, const uint2 ub, size_t i) {
+    const float2 ua = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub.x));
+    const float2 uc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub.y));
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(d.x * act_grad_exact(ua.x, act), d.y * act_grad_exact(ua.y, act));
+    const __nv_bfloat162 hi = __floats2bfloat162_rn(d.z * act_grad_exact(uc.x, act), d.w * act_grad_exact(uc.y, act));
+    uint2 pk;
+    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(du + i) = pk;
+    const float2 fl = __bfloat1622float2(lo), fh = __bfloat1622float2(hi);
+    s0 += fl.x; s1 += fl.y; s2 += fh.x; s3 += fh.y;
+  };
   int r = r0;
-  for (; r + 4 <= r1; r += 4) {                 // four independent rows in flight per thread
-    float d[4], uu[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const size_t i = static_cast<size_t>(r + k) * C + c;
-      d[k] = dg[i];
-      uu[k] = __bfloat162float(u[i]);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const __nv_bfloat16 v = __float2bfloat16_rn(d[k] * act_grad_exact(uu[k], act));
-      du[static_cast<size_t>(r + k) * C + c] = v;
-      s += __bfloat162float(v);
-    }
+  for (; r + 2 <= r1; r += 2) {                 // two independent rows in flight per thread
+    const size_t i0 = static_cast<size_t>(r) * C + c, i1 = i0 + C;
+    const float4 d0 = *reinterpret_cast<const float4*>(dg + i0), d1 = *reinterpret_cast<const float4*>(dg + i1);
+    const uint2 u0 = *reinterpret_cast<const uint2*>(u + i0), u1 = *reinterpret_cast<const uint2*>(u + i1);
+    one(d0, u0, i0);
+    one(d1, u1, i1);
   }
-  for (; r < r1; ++r) {
+  if (r < r1) {
     const size_t i = static_cast<size_t>(r) * C + c;
-    const __nv_bfloat16 v = __float2bfloat16_rn(dg[i] * act_grad_exact(__bfloat162float(u[i]), act));
-    du[i] = v;
-    s += __bfloat162float(v);
+    one(*reinterpret_cast<const float4*>(dg + i), *reinterpret_cast<const uint2*>(u + i), i);
   }
-  if (colsum && r1 > r0) atomicAdd(colsum + c, s);
+  if (colsum && r1 > r0) {
+    atomicAdd(colsum + c, s0); atomicAdd(colsum + c + 1, s1); atomicAdd(colsum + c + 2, s2); atomicAdd(colsum + c + 3, s3);
+  }
 }
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
