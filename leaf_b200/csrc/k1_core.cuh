@@ -4,12 +4,19 @@
 //
 // Follows, step by step:
 //   edit rule          /root/reference/utils_attacks.py:169-213 (generate_sentence, alternative = -1)
-//   basic_clean        /root/reference/src/open_clip/tokenizer.py:66-69  (ftfy = identity on the ASCII domain,
+//   basic_clean        /root/reference/src/open_clip/tokenizer.py:66-69  (ftfy = identity on the domain below,
 //                      html.unescape twice, strip)
 //   whitespace_clean   tokenizer.py:72-75      lower: tokenizer.py:83-85
 //   regex split        tokenizer.py:160-163    bpe: tokenizer.py:172-211     row layout: tokenizer.py:256-263
 // html.unescape is CPython's Lib/html/__init__.py (_charref regex + _replace_charref) restated on code points
-// <= U+00FF, the closed domain of one edit on an ASCII caption; anything that leaves it raises a status flag.
+// <= U+00FF. Domain: UTF-8 captions whose code points are all <= U+00FF (ASCII + Latin-1 Supplement: accented Western
+// European text), one LEAF edit, and whatever the two unescape passes make of that while staying <= U+00FF. Text is held
+// one byte per code point internally. Everything outside raises a status flag (the host raises LeafError), never a
+// silently different row: code points > U+00FF / malformed UTF-8; and the inputs on which ftfy.fix_text - which the
+// reference runs first and which cannot be restated here - is NOT the identity: C1 controls U+0080..U+009F (ftfy maps
+// them to Windows-1252), a UTF-8-lead-like character followed by a continuation-like one (`Ã©`: ftfy re-decodes
+// mojibake), a third level of entity nesting and ALL-CAPS entity names (`&EACUTE;`) in text without '<' (ftfy unescapes
+// one level itself, with upper-case variants html.unescape does not know).
 #pragma once
 #include <stdint.h>
 
@@ -27,7 +34,7 @@ constexpr int K1_CTX = 77;
 constexpr int K1_SOT = 49406, K1_EOT = 49407;
 constexpr uint16_t K1_UNSUP_V = 0xFFFF, K1_EMPTY_V = 0xFFFE;
 constexpr uint16_t K1_NO_RANK = 0xFFFF, K1_DIRTY = 0xFFFE;
-constexpr int K1_FLAG_ENTITY_DOMAIN = 1, K1_FLAG_NON_ASCII = 2, K1_FLAG_TOO_LONG = 4;
+constexpr int K1_FLAG_ENTITY_DOMAIN = 1, K1_FLAG_NON_ASCII = 2 /* outside U+0000..U+00FF, or ftfy would rewrite it */, K1_FLAG_TOO_LONG = 4;
 constexpr uint64_t K1_SLOT_EMPTY = ~0ull;
 
 struct K1Tables {
@@ -73,6 +80,25 @@ K1_HD uint32_t k1_merge_rank(const K1Tables& T, uint32_t left, uint32_t right) {
     if (static_cast<uint32_t>(e >> 32) == key) return static_cast<uint32_t>(e & 0xFFFFu);
     slot = (slot + 1u) & mask;
   }
+}
+
+// ---- UTF-8 -> one byte per code point (U+0000..U+00FF); out may alias in (never longer than the input) -----
+K1_HD int k1_decode_utf8(const uint8_t* in, int n, uint8_t* out, int* flags) {
+  int m = 0;
+  for (int i = 0; i < n;) {
+    const uint8_t b = in[i];
+    if (b < 0x80) { out[m++] = b; ++i; }
+    else if ((b == 0xC2 || b == 0xC3) && i + 1 < n && (in[i + 1] & 0xC0) == 0x80) {
+      out[m++] = static_cast<uint8_t>(((b & 3) << 6) | (in[i + 1] & 0x3F));
+      i += 2;
+    } else {                                                // > U+00FF or malformed: flagged, one '?' per sequence
+      *flags |= K1_FLAG_NON_ASCII;
+      out[m++] = '?';
+      ++i;
+      while (i < n && (in[i] & 0xC0) == 0x80) ++i;
+    }
+  }
+  return m;
 }
 
 // ---- edit rule (utils_attacks.py:169-213) ---------------------------------------------
@@ -128,7 +154,7 @@ K1_HD int k1_emit_cp(uint16_t v, uint8_t* out, int m, int* flags) {
   return m;
 }
 
-K1_HD int k1_unescape(const K1Tables& T, const uint8_t* in, int n, uint8_t* out, int* flags) {
+K1_HD int k1_unescape(const K1Tables& T, const uint8_t* in, int n, uint8_t* out, int* flags, bool ftfy_caps = false) {
   int m = 0, i = 0;
   while (i < n) {
     const uint8_t ch = in[i];
@@ -179,6 +205,15 @@ K1_HD int k1_unescape(const K1Tables& T, const uint8_t* in, int n, uint8_t* out,
     if (e >= 0) {
       m = k1_emit_cp(T.ent_val[e], out, m, flags);
     } else {
+      if (ftfy_caps && sl >= 3 && s[sl - 1] == ';') {         // &EACUTE; - ftfy knows upper-case variants, html.unescape does not
+        bool caps = true, letter = false;
+        for (int k = 0; k + 1 < sl; ++k) {
+          const uint8_t c = s[k];
+          if (c >= 'A' && c <= 'Z') letter = true;
+          else if (!(c >= '0' && c <= '9')) { caps = false; break; }
+        }
+        if (caps && letter) *flags |= K1_FLAG_ENTITY_DOMAIN;
+      }
       int x = sl - 1;
       for (; x > 1; --x) {
         e = k1_find_entity(T, s, x);
@@ -259,20 +294,35 @@ K1_HD int k1_split(const K1Tables& T, const uint8_t* t, int n, uint16_t* piece_s
 // instead of treating as white space) are outside the domain and flagged.
 K1_HD int k1_prepare(const K1Tables& T, const uint8_t* src, int len, bool do_edit, int z, int c, K1Scratch& S, bool hf = false) {
   int flags = 0;
-  int n;
-  if (do_edit) n = k1_apply_edit(src, len, z, c, S.buf_a);
-  else { for (int i = 0; i < len; ++i) S.buf_a[i] = src[i]; n = len; }
-  bool amp = false;
+  int n = k1_decode_utf8(src, len, S.buf_b, &flags);       // code points, one byte each
+  if (do_edit && (z < 0 || z > 2 * n)) { do_edit = false; flags |= K1_FLAG_TOO_LONG; }
+  if (do_edit) n = k1_apply_edit(S.buf_b, n, z, c, S.buf_a);
+  else for (int i = 0; i < n; ++i) S.buf_a[i] = S.buf_b[i];
+  bool amp = false, lt = false;
   for (int i = 0; i < n; ++i) {
-    if (S.buf_a[i] & 0x80) flags |= K1_FLAG_NON_ASCII;
-    if (hf && (S.buf_a[i] == 0x7f || (S.buf_a[i] < 0x20 && S.buf_a[i] != 9 && S.buf_a[i] != 10 && S.buf_a[i] != 13))) flags |= K1_FLAG_NON_ASCII;
-    amp |= (S.buf_a[i] == '&');
+    const uint8_t ch = S.buf_a[i];
+    if (ch & 0x80) {
+      if (hf) flags |= K1_FLAG_NON_ASCII;                   // HF mode stays ASCII: BasicTokenizer drops U+00AD and other controls
+      else if (ch <= 0x9F) flags |= K1_FLAG_NON_ASCII;      // C1 control: ftfy rewrites it as Windows-1252
+      else if (ch >= 0xC2 && ch <= 0xF4 && i + 1 < n && S.buf_a[i + 1] >= 0x80 && S.buf_a[i + 1] <= 0xBF)
+        flags |= K1_FLAG_NON_ASCII;                         // looks like UTF-8 read as Latin-1: ftfy re-decodes it
+    }
+    if (hf && (ch == 0x7f || (ch < 0x20 && ch != 9 && ch != 10 && ch != 13))) flags |= K1_FLAG_NON_ASCII;
+    amp |= (ch == '&');
+    lt |= (ch == '<');
   }
   if (hf) amp = false;
   const uint8_t* cur = S.buf_a;
   if (amp) {                                               // html.unescape(html.unescape(text))
-    n = k1_unescape(T, S.buf_a, n, S.buf_b, &flags);
+    n = k1_unescape(T, S.buf_a, n, S.buf_b, &flags, !lt);
     n = k1_unescape(T, S.buf_b, n, S.buf_a, &flags);
+    if (!lt) {                                             // ftfy.fix_text unescapes one level first when the text has no '<':
+      int f3 = 0;                                          // the reference then sees three levels; exact here iff the third is a no-op
+      const int n3 = k1_unescape(T, S.buf_a, n, S.buf_b, &f3);
+      bool same = n3 == n;
+      for (int i = 0; same && i < n; ++i) same = S.buf_a[i] == S.buf_b[i];
+      if (!same) flags |= K1_FLAG_ENTITY_DOMAIN;
+    }
   }
   n = k1_clean(T, cur, n, S.buf_b);
   S.text_len = n;

@@ -1,4 +1,5 @@
-// K1 kernel: candidate expansion + CLIP BPE tokenization, one warp per candidate (sm_100a).
+// K1 kernel: candidate expansion + CLIP BPE tokenization, one warp per candidate (sm_100a). Captions are UTF-8 with code
+// points <= U+00FF (k1_core.cuh: domain); edit positions count code points, as Python's str does.
 //   lanes 0..31 copy the caption into shared memory with 16-byte loads when the source is aligned,
 //   lane 0 applies the edit, unescapes, cleans and splits (serial, a few hundred byte operations),
 //   lanes take regex pieces round-robin and run the BPE merge loop on them (merge ranks from an L2-resident
@@ -68,8 +69,7 @@ __global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32) k1_expand_tokenize_kern
     int z = 0, c = -1;
     if (a.n > 0 && !is_base) {
       z = a.sel ? a.pos[b * a.n + a.sel[b]] : a.pos[r];
-      c = a.chr[r];
-      if (z < 0 || z > 2 * len) { edit = false; flags |= K1_FLAG_TOO_LONG; }
+      c = a.chr[r];                                        // k1_prepare checks z against the number of code points
     }
     flags |= k1_prepare(T, s_src[w], len, edit, z, c, S, a.hf_mode != 0);
     s_meta[w][0] = S.text_len;

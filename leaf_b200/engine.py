@@ -169,14 +169,15 @@ class LeafEngine:
     # ---- K1 ----------------------------------------------------------------------------------------------
     @staticmethod
     def pack_captions(sentences):
-        """list[str] -> (uint8 caption bytes back to back, int32 [B+1] offsets). The buffer tail is padded so the
-        kernel's 16-byte loads never leave the allocation."""
+        """list[str] -> (uint8 caption bytes back to back, int32 [B+1] BYTE offsets). Captions travel as UTF-8; the kernel's
+        domain is code points <= U+00FF (ASCII + Latin-1 Supplement; csrc/k1_core.cuh), checked here for a clear message and
+        again on the device. The buffer tail is padded so the kernel's 16-byte loads never leave the allocation."""
         blobs = []
         for s in sentences:
-            try:
-                b = s.encode("ascii")
-            except UnicodeEncodeError as ex:
-                raise LeafError(f"caption outside the tokenizer kernel's ASCII domain: {s!r}") from ex
+            if not s.isascii() and max(map(ord, s)) > 0xFF:
+                bad = next(c for c in s if ord(c) > 0xFF)
+                raise LeafError(f"caption outside the tokenizer kernel's domain (code points <= U+00FF): U+{ord(bad):04X} in {s!r}")
+            b = s.encode("utf-8")
             if len(b) > MAX_CAPTION_BYTES:
                 raise LeafError(f"caption longer than {MAX_CAPTION_BYTES} bytes")
             blobs.append(b)
@@ -237,8 +238,11 @@ class LeafEngine:
         st = int(self._status.item())
         if st:
             self._status.zero_()
-            what = [m for bit, m in ((1, "an html entity expanded outside U+0000..U+00FF"),
-                                     (2, "non-ASCII caption byte"), (4, "caption too long / position out of range"),
+            what = [m for bit, m in ((1, "an html entity expanded outside U+0000..U+00FF, or entity text ftfy would unescape differently "
+                                         "(third nesting level / ALL-CAPS name)"),
+                                     (2, "text outside the kernel's domain: code point > U+00FF, a C1 control, a Latin-1 sequence ftfy "
+                                         "would re-decode as mojibake, or any non-ASCII byte in HF-tokenizer mode / the --constrain filter"),
+                                     (4, "caption too long / position out of range"),
                                      (8, "sentence longer than the constraint filter accepts (511 bytes)"),
                                      (16, "constraint filter buffer overflow")) if st & bit]
             raise LeafError("tokenizer kernel: " + "; ".join(what))

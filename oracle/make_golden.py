@@ -106,6 +106,41 @@ def gen_tokenizer():
     print("tokenizer strings", len(enc))
 
 
+LATIN1_CAPTIONS = [
+    "un café crème à la française", "Ein schöner Tag in München mit Straße und Fluß", "El niño comió jalapeños en Ávila",
+    "ÉCOLE SUPÉRIEURE DE LYON À PARIS", "Ærøskøbing er en by på Ærø", "naïve façade coöperate résumé", "señor Ñandú's piñata isn't here",
+    "µm and ªº ordinals 1º 2ª", "½ cup ¼ tsp ¾ oz ¹²³ x²", "3×4÷2 ±1 °C §5 ¶ © ® «quoted» ¿qué? ¡hola!", "ÿ y-less þorn Þing ðat Ðe",
+    "a\u00a0b non\u00a0breaking  spaces\u00a0", "Crème brûlée's déjà-vu: voilà!it's", "ß", "É", "éé 12½x ·middle· ¬not ¦bar ¨uml ¯macr ´acute ¸cedil",
+    "soft\u00adhyphen in\u00adside", "£5 ¥6 ¢7 ¤8 and 9€-less", "Ò Ó Ô Õ Ö Ø Ù Ú Û Ü Ý à á â ã ä å æ ç è é ê ë ì í î ï ð ñ ò ó ô õ ö ø ù ú û ü ý þ ÿ",
+    "À Á Â Ã Ä Å Æ Ç È É Ê Ë Ì Í Î Ï Ð Ñ", "façade&amp;café &eacute;t&eacute; &Eacute;T&Eacute; &#233; &#xE9;", "l'été d'août m'a plu 's 't 're",
+]
+
+
+def gen_tokenizer_latin1():
+    """Captions with code points in U+0080..U+00FF (the Latin-1 Supplement K1 accepts as UTF-8 input): the reference's
+    SimpleTokenizer on the captions and on attack-shaped edits of them (utils_attacks.generate_sentence, positions counted in
+    code points). ftfy is the identity shim here, as for every other fixture; K1 flags the Latin-1 inputs on which the real
+    ftfy would not be (C1 controls, mojibake-shaped pairs) and none of these captions is one of them, except the pairs an
+    edit can create by deleting the character between a lead-like and a continuation-like one - those cases are kept in the
+    fixture (their token ids are still what SimpleTokenizer produces under the shim) and marked."""
+    tok = open_clip.get_tokenizer("ViT-L-14")
+    rng = random.Random(23)
+    caps = [c for c in LATIN1_CAPTIONS if c.isascii() or max(map(ord, c)) <= 0xFF]
+    assert len(caps) == len(LATIN1_CAPTIONS) - 1                                   # the one with the euro sign is dropped
+    enc = [[t, tok.encode(t)] for t in caps]
+    edits = []
+    for S in caps:
+        for _ in range(16):
+            z = rng.randint(0, 2 * len(S))
+            u = rng.randrange(len(V))
+            out = utils_attacks.generate_sentence(S, z, u, V, 1, alternative=-1)
+            edits.append([S, z, V[u], out, tok.encode(out)])
+    rows = tok(caps).tolist()
+    json.dump({"encode": enc, "edits": edits, "rows_in": caps, "rows": rows},
+              open(os.path.join(OUT, "tokenizer_latin1_golden.json"), "w"))
+    print("latin-1 tokenizer strings", len(enc), "edits", len(edits))
+
+
 def build_ref_clip(cfg: synth.TowerCfg, sd):
     model = CLIP(embed_dim=cfg.embed_dim,
                  vision_cfg=CLIPVisionCfg(layers=1, width=64, head_width=32, patch_size=16, image_size=32),
@@ -292,6 +327,9 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["convert_ids"]:                       # add this fixture without regenerating the others
         gen_convert_ids()
         sys.exit(0)
+    if sys.argv[1:] == ["latin1"]:
+        gen_tokenizer_latin1()
+        sys.exit(0)
     gen_convert_ids()
     gen_edit()
     gen_tokenizer()
@@ -299,3 +337,4 @@ if __name__ == "__main__":
     gen_attack()
     gen_eval_attacks()
     gen_hf_tokenizer()
+    gen_tokenizer_latin1()

@@ -31,7 +31,7 @@ def lib():
     return _lib
 
 
-def pack_captions(caps, encoding="ascii"):
+def pack_captions(caps, encoding="utf-8"):
     blobs = [c.encode(encoding) for c in caps]
     off = np.zeros(len(caps) + 1, dtype=np.int32)
     off[1:] = np.cumsum([len(b) for b in blobs])
@@ -39,7 +39,7 @@ def pack_captions(caps, encoding="ascii"):
     return data, off
 
 
-def expand_tokenize(caps, n=0, pos=None, chr_=None, sel=None, valid=None, encoding="ascii", hf=False):
+def expand_tokenize(caps, n=0, pos=None, chr_=None, sel=None, valid=None, encoding="utf-8", hf=False):
     """Returns (tokens [R,77] int32, lengths [R] int32, flags)."""
     L = lib()
     L.k1h_set_mode(1 if hf else 0)

@@ -222,6 +222,38 @@ def test_k1_golden_strings(eng, golden_dir):
     assert tok.tolist() == g["rows"]
 
 
+def test_k1_latin1_utf8_captions(eng, golden_dir):
+    """Accented captions (UTF-8, code points <= U+00FF) on the device: the reference's SimpleTokenizer rows, attack-shaped
+    edits with positions counted in code points, the whole attack on such captions, and LeafError beyond the domain."""
+    from leaf_b200 import LeafError, attack_text_leaf
+    g = json.load(open(os.path.join(golden_dir, "tokenizer_latin1_golden.json")))
+    assert eng.tokenize(g["rows_in"]).cpu().tolist() == g["rows"]
+    by_s = {}
+    for S, z, c, out, ids in g["edits"]:
+        by_s.setdefault(S, []).append((z, c, ids))
+    for S, cases in by_s.items():
+        pos = np.array([[c[0] for c in cases]], dtype=np.int32)
+        chr_ = np.array([[c[1] for c in cases]], dtype=np.int32)
+        tok, ln = _k1(eng, [S], len(cases), pos, chr_)
+        for j, (_, _, ids) in enumerate(cases):
+            want = ([49406] + ids + [49407])[:77]
+            want[-1] = 49407
+            assert tok[j, :len(want)].tolist() == want and not tok[j, len(want):].any(), (S, cases[j])
+    eng._status.zero_()
+    caps = g["rows_in"][:6]
+    anchor = eng.encode_tokens(eng.tokenize(caps)) + 0.1
+    np.random.seed(3)
+    feats, adv = attack_text_leaf(eng, None, caps, anchor, "cuda", n=12, k=2)
+    assert all(abs(len(a) - len(c)) <= 2 for a, c in zip(adv, caps)) and adv != caps
+    assert torch.equal(eng.encode_tokens(eng.tokenize(adv)), feats)
+    for bad in ("\u0141\u00f3d\u017a", "emoji \U0001F600"):
+        with pytest.raises(LeafError, match="U\\+00FF"):
+            eng.tokenize([bad])
+    with pytest.raises(LeafError, match="domain"):
+        eng.tokenize(["mojibake Ã©"])
+    eng._status.zero_()
+
+
 def test_k1_candidates_bit_exact(eng):
     from leaf_b200 import synth
     from oracle import leaf_oracle as O

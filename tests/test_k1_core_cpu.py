@@ -40,14 +40,14 @@ def test_golden_tokenizer_strings(golden_dir):
         if texts and texts[-1] is text:
             want.append(_row(ids))
     assert len(texts) > 2500
-    tok, ln, flags = H.expand_tokenize(texts, encoding="latin-1")
+    tok, ln, flags = H.expand_tokenize(texts)
     want = np.array(want, dtype=np.int32)
     bad = np.nonzero((tok != want).any(axis=1))[0]
     assert len(bad) == 0, [(texts[i], tok[i][:12].tolist(), want[i][:12].tolist()) for i in bad[:5]]
     assert (ln == want.argmax(axis=1) + 1).all()
     # entity expansions that leave U+0000..U+00FF must be flagged, never silently mis-tokenized
     for t in unsup:
-        _, _, fl = H.expand_tokenize([t], encoding="latin-1")
+        _, _, fl = H.expand_tokenize([t])
         assert fl & 1, t
     rows_in = [r for r in g["rows_in"]]
     tok, ln, _ = H.expand_tokenize(rows_in)
@@ -135,3 +135,53 @@ def test_hf_mode_matches_transformers(golden_dir):
         assert not tok[i, len(want):].any()
         assert ln[i] == want.index(49407) + 1                    # pooled position: the FIRST EOS (argmax)
     H.expand_tokenize(["x"])                                  # back to the default mode for the other tests
+
+
+def _ftfy_risk(text):
+    """The Latin-1 inputs K1 flags because the real ftfy.fix_text would rewrite them (csrc/k1_core.cuh: domain)."""
+    for i, ch in enumerate(text):
+        o = ord(ch)
+        if 0x80 <= o <= 0x9F:
+            return True
+        if 0xC2 <= o <= 0xF4 and i + 1 < len(text) and 0x80 <= ord(text[i + 1]) <= 0xBF:
+            return True
+    return False
+
+
+def test_latin1_utf8_captions_golden(golden_dir):
+    """UTF-8 captions with code points up to U+00FF (accented Western European text): the reference's SimpleTokenizer on the
+    captions and on attack-shaped edits whose positions count CODE POINTS (tests/golden/tokenizer_latin1_golden.json, generated
+    from the reference by oracle/make_golden.py latin1); the domain flags for everything beyond."""
+    g = json.load(open(os.path.join(golden_dir, "tokenizer_latin1_golden.json")))
+    texts = [t for t, _ in g["encode"]]
+    assert sum(not t.isascii() for t in texts) >= 18
+    tok, ln, flags = H.expand_tokenize(texts)
+    want = np.array([_row(ids) for _, ids in g["encode"]], dtype=np.int32)
+    assert (tok == want).all(), [t for t, a, b in zip(texts, tok, want) if (a != b).any()]
+    assert (ln == want.argmax(axis=1) + 1).all()
+    assert tok.tolist() == g["rows"] and flags == 0
+    by_s = {}
+    for S, z, c, out, ids in g["edits"]:
+        by_s.setdefault(S, []).append((z, c, out, ids))
+    n_risky = 0
+    for S, cases in by_s.items():
+        tok, ln, flags = H.expand_tokenize([S], n=len(cases), pos=[c[0] for c in cases], chr_=[c[1] for c in cases])
+        for j, (z, c, out, ids) in enumerate(cases):
+            assert out == O.edit_sentence(S, z, c)
+            assert tok[j].tolist() == _row(ids), (S, z, c, out)
+            _, _, fl = H.expand_tokenize([out])
+            n_risky += _ftfy_risk(out)
+            assert bool(fl & 2) == _ftfy_risk(out), (out, fl)
+    # outside the domain: loud, never a silently different row
+    for bad, bit in (("na\u00efve \u0141\u00f3d\u017a", 2), ("caf\u00e9 \u2019s", 2), ("emoji \U0001F600", 2), ("a\u0085b", 2), ("Ã©t\u00e9", 2),
+                     ("x &amp;amp;lt; y", 1), ("x &EACUTE; y", 1), ("ok &amp;lt; <b>", 0), ("caf\u00e9 &eacute;", 0)):
+        _, _, fl = H.expand_tokenize([bad])
+        assert (fl & 3) == bit, (bad, fl)
+    # invalid UTF-8 bytes are flagged as well
+    data = np.frombuffer(b"ab\xff\xc3" + b"\0", dtype=np.uint8).copy()
+    off = np.array([0, 4], dtype=np.int32)
+    L = H.lib()
+    import ctypes
+    t, l = np.zeros((1, 77), dtype=np.int32), np.zeros(1, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert L.k1h_expand_tokenize(p(data), p(off), 1, 0, None, None, None, None, p(t), p(l)) & 2
