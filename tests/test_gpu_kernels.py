@@ -281,10 +281,14 @@ def test_k1_candidates_bit_exact(eng):
 
 def test_k1_flags_out_of_domain(eng):
     from leaf_b200 import LeafError
+    from oracle import leaf_oracle as O
+    assert torch.equal(eng.tokenize(["café"]).cpu(), O.OracleTokenizer()(["café"]))       # Latin-1 is inside the domain now
     with pytest.raises(LeafError):
-        eng.tokenize(["café"])
+        eng.tokenize(["caf\u00e9 \u0142"])                                                 # U+0142 is not
     with pytest.raises(LeafError):
         eng.tokenize(["x &lambda; y"])
+    with pytest.raises(LeafError):
+        eng.tokenize(["x &amp;amp;lt; y"])                                                 # ftfy would unescape a third level
     assert eng.tokenize(["x &lt; y"]).shape == (1, 77)
 
 
