@@ -4,7 +4,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libleaf_b200.so")
+LIB_PATH = os.environ.get("LEAF_B200_LIB") or os.path.join(HERE, "lib", "libleaf_b200.so")   # the override is for same-box A/B runs of two builds
 
 c_int, c_void_p, c_float, c_i64 = ctypes.c_int32, ctypes.c_void_p, ctypes.c_float, ctypes.c_int64
 

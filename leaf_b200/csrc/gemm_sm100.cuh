@@ -175,20 +175,18 @@ __device__ __forceinline__ float fast_rcp(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// nn.GELU (erf form): x Phi(x) = max(x, 0) - g,  g = 0.5 |x| erfc(|x| / sqrt 2) >= 0.
-// erfc(z) = poly(t) exp(-z^2), t = 1 / (1 + p z) (Abramowitz-Stegun 7.1.26, |error| <= 1.5e-7 on erf); evaluated on |x|
-// so the negative tail has no cancellation. The 0.5 and the 1/sqrt 2 are folded into the constants:
-// 12 FP32 ops + 2 MUFU per element (libdevice's erff costs ~39 instructions and paced the fc1 GEMM, profiles/r1).
+// nn.GELU (erf form) x Phi(x), written as x sigmoid(q(x)) with q(x) = x (c0 + c1 x^2 + c2 x^4) an odd polynomial fitted to
+// 2 atanh(erf(x / sqrt 2)) (x^2 clamped at 36, beyond which sigmoid is 1 or 0 to 1e-9): 7 FP32 ops + 2 MUFU per element, the
+// cost of QuickGELU plus three. No cancellation anywhere (the negative tail is a product, not a difference), so the error
+// is the fit's: |error| <= 7e-5 absolute, relative 4e-4 where |y| > 0.01, 3e-3 where |y| > 0.001 - at or below the bf16
+// rounding the result gets anyway (2^-9 relative); tools/fit_gelu.py reproduces the coefficients and these bounds.
+// Before: max(x, 0) - 0.5 |x| erfc(|x| / sqrt 2) with Abramowitz-Stegun 7.1.26 (13 FP32 + 2 MUFU, |error| 1.5e-7) - exact
+// beyond need for a bf16 result, and the fc1 GEMM ran 13 % below the QKV GEMM's rate per FLOP in situ because its
+// epilogue's FP32 / MUFU work costs power under the board's cap; libdevice's erff (~39 instructions) before that.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float a = fabsf(x);
-  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752440f, a, 1.0f));
-  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
-  poly = fmaf(t, poly, 0.5f * 1.421413741f);
-  poly = fmaf(t, poly, 0.5f * -0.284496736f);
-  poly = fmaf(t, poly, 0.5f * 0.254829592f);
-  const float e = fast_ex2(a * -0.72134752044448170368f * a);            // exp(-x^2 / 2)
-  const float g = (poly * t) * (a * e);
-  return fmaxf(x, 0.f) - g;
+  const float x2 = fminf(x * x, 36.0f);
+  const float r = fmaf(x2, fmaf(x2, 0.0011236976601259265f, -0.10762115607988151f), -2.299969046114191f);   // -log2(e) q(x) / x
+  return x * fast_rcp(1.0f + fast_ex2(x * r));
 }
 __device__ __forceinline__ float quick_gelu(float x) {                   // x sigmoid(1.702 x), transformer.py:33-36
   return x * fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));
