@@ -196,6 +196,9 @@ int leaf_backward(leaf_handle_t h, int64_t generation, const float* dfeat, int32
  * second stream can all-reduce that slice while the backward of the layers below still runs. fn == NULL removes it. */
 typedef void (*leaf_backward_hook_t)(int32_t layer, void* user);
 int leaf_set_backward_hook(leaf_handle_t h, leaf_backward_hook_t fn, void* user);
+/* Cap the persistent GEMM grids at n_sms SMs (0 = the whole device) so that a collective's CTAs find SMs of their own while
+ * it runs next to the backward. */
+int leaf_set_sm_budget(leaf_handle_t h, int32_t n_sms);
 
 /* AdamW (torch.optim.AdamW semantics, decoupled weight decay) over the tower's parameters held in ONE flat fp32 buffer
  * (train_AT_text_only.py:326-341: the gain / bias / LayerNorm group with weight_decay 0 is laid out first, elements
@@ -206,6 +209,9 @@ int leaf_adamw(leaf_handle_t h, float* params, const float* grads, float* exp_av
                int64_t n_nodecay, float lr, float beta1, float beta2, float eps, float weight_decay, int32_t step,
                float grad_scale, void* stream);
 int leaf_sumsq(leaf_handle_t h, const float* g, int64_t n, float* out, void* stream);
+/* g[0, n) *= s in place (n a multiple of 4): the rescale of torch.nn.utils.clip_grad_norm_ on the ACCUMULATED gradients
+ * after a micro-batch that is not followed by an optimizer step - utils_AT.py:356-357 clips after every micro-batch. */
+int leaf_scale(leaf_handle_t h, float* g, int64_t n, float s, void* stream);
 
 /* ---- test / bench hooks (used by tests/ and bench.py only) ------------------------------------ */
 /* C[M,N] = A[M,K] . Bt[N,K]^T (+bias[N]) with the tower's tcgen05 kernel. epilogue: 0 = bf16 store,

@@ -49,9 +49,11 @@ SIGNATURES = {
     "leaf_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, ctypes.POINTER(c_i64), c_void_p]),
     "leaf_backward": (c_int, [c_void_p, c_i64, c_void_p, c_int, ctypes.POINTER(LeafWeightPtrs), c_void_p]),
     "leaf_set_backward_hook": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "leaf_set_sm_budget": (c_int, [c_void_p, c_int]),
     "leaf_adamw": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_i64, ctypes.c_float, ctypes.c_float,
                            ctypes.c_float, ctypes.c_float, ctypes.c_float, c_int, ctypes.c_float, c_void_p]),
     "leaf_sumsq": (c_int, [c_void_p, c_void_p, c_i64, c_void_p, c_void_p]),
+    "leaf_scale": (c_int, [c_void_p, c_void_p, c_i64, ctypes.c_float, c_void_p]),
     "leaf_gemm_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                c_void_p, c_void_p]),
     "leaf_gemm_bf16_mn": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),

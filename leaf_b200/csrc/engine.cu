@@ -110,6 +110,7 @@ struct leaf_engine {
   float* xc = nullptr;                // [max_seqs, W] fp32 residual rows of the pooled positions (final layer, compact)
   int* first_of = nullptr;            // [max_seqs] sequence whose rows stand for sequence i
   bool prune_last = true;             // final layer: out-proj + MLP on the pooled rows only
+  int gemm_sm_budget = 0;             // > 0: the persistent GEMM grids use at most this many SMs (leaf_set_sm_budget)
   int att_impl = 1;                   // 1 = register-fed attention_kernel (default: faster in situ), 2 = cp.async ring attention2_kernel (LEAF_ATTENTION_IMPL=2)
   int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr, *dup_of = nullptr, *need = nullptr;
   int4* meta = nullptr;
@@ -218,7 +219,7 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   p.M = M; p.m_dev = m_dev; p.N = N; p.K = K; p.bias = bias; p.C = C; p.ldc = ldc; p.act = act; p.delta = delta;
   const int m_tiles = (M + GEMM2_BM - 1) / GEMM2_BM, n_tiles = (N + GEMM_BN - 1) / GEMM_BN;
   long tiles = static_cast<long>(m_tiles) * n_tiles;
-  const int pairs_cap = e->sm_count / 2;
+  const int pairs_cap = ((e->gemm_sm_budget > 0 && e->gemm_sm_budget < e->sm_count) ? e->gemm_sm_budget : e->sm_count) / 2;
   if (allow_split_k && epi == EPI_F32_RESIDUAL && !bias && !delta && !res && !m_dev && tiles < pairs_cap) {
     // C += A.B with few output tiles and a long contraction (the weight gradients: 16-64 tiles, K = packed rows): divide the
     // k-blocks over several work units so that the launch fills the 74 CTA pairs; cost model = waves x (k-blocks per part +
@@ -967,6 +968,15 @@ extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* d
   return LEAF_OK;
 }
 
+// The persistent GEMM grids normally take every SM (one CTA pair per TPC). While a collective runs next to the backward
+// (leaf_set_backward_hook + an all-reduce on a side stream) its CTAs need SMs of their own: n_sms > 0 caps the GEMM grids at
+// n_sms SMs, 0 restores the full device.
+extern "C" int leaf_set_sm_budget(leaf_handle_t e, int32_t n_sms) {
+  if (!e || n_sms < 0) return fail(LEAF_ERR_INVALID, "bad argument");
+  e->gemm_sm_budget = n_sms >= 2 ? n_sms : 0;
+  return LEAF_OK;
+}
+
 extern "C" int leaf_set_backward_hook(leaf_handle_t e, leaf_backward_hook_t fn, void* user) {
   if (!e) return fail(LEAF_ERR_INVALID, "null handle");
   e->bwd_hook = fn;
@@ -998,6 +1008,16 @@ extern "C" int leaf_adamw(leaf_handle_t e, float* params, const float* grads, fl
 extern "C" int leaf_sumsq(leaf_handle_t e, const float* g, int64_t n, float* out, void* stream) {
   if (!e || !g || !out || n <= 0 || n % 4 != 0) return fail(LEAF_ERR_INVALID, "bad argument");
   sumsq_kernel<<<launch_ew(e, static_cast<size_t>(n) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, static_cast<size_t>(n), out);
+  e->launches++;
+  CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+// g[0, n) *= s (in place): torch.nn.utils.clip_grad_norm_'s rescale of the accumulated gradients after a micro-batch that
+// is not followed by an optimizer step (utils_AT.py:356-357 runs it after EVERY micro-batch)
+extern "C" int leaf_scale(leaf_handle_t e, float* g, int64_t n, float s, void* stream) {
+  if (!e || !g || n <= 0 || n % 4 != 0) return fail(LEAF_ERR_INVALID, "bad argument");
+  scale_f32_kernel<<<launch_ew(e, static_cast<size_t>(n) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, static_cast<size_t>(n), s);
   e->launches++;
   CK(cudaGetLastError());
   return LEAF_OK;

@@ -68,6 +68,13 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     atomicAdd(colsum + c, s0); atomicAdd(colsum + c + 1, s1); atomicAdd(colsum + c + 2, s2); atomicAdd(colsum + c + 3, s3);
   }
 }
+__global__ void scale_f32_kernel(float* __restrict__ g, size_t n, float s) {
+  for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i + 3 < n; i += static_cast<size_t>(gridDim.x) * blockDim.x * 4) {
+    float4 v = *reinterpret_cast<float4*>(g + i);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    *reinterpret_cast<float4*>(g + i) = v;
+  }
+}
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
     dst[i] = __float2bfloat16_rn(src[i]);

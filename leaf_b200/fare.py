@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes
 import math
+import os
 import weakref
 
 import torch
@@ -30,7 +31,7 @@ class FareTrainer:
     def __init__(self, tower: LeafTextTower, frozen: LeafTextTower, V=V_DEFAULT, rho: int = 50, k_adv: int = 1, lr: float = 1e-5,
                  wd: float = 1e-4, beta1: float = 0.9, beta2: float = 0.98, eps: float = 1e-6, accum_freq: int = 1,
                  grad_clip_norm: float = None, constrain=False, normalize_fare: bool = False, use_charmer: bool = False,
-                 group=None, overlap_allreduce: bool = True):
+                 group=None, overlap_allreduce: bool = True, backward_sm_budget: int = None):
         self.tower, self.frozen, self.V = tower, frozen, list(V)
         self.rho, self.k_adv, self.constrain = rho, k_adv, constrain
         self.lr, self.wd, self.beta1, self.beta2, self.eps = lr, wd, beta1, beta2, eps
@@ -50,6 +51,8 @@ class FareTrainer:
         self._distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
         self.overlap_allreduce = bool(overlap_allreduce) and self._distributed
         self._works, self._reduced = [], False
+        # SMs the backward's persistent GEMM grids may take while the exchange runs beside them (None: all of them)
+        self.backward_sm_budget = int(os.environ.get("LEAF_BACKWARD_SM_BUDGET", "0")) if backward_sm_budget is None else int(backward_sm_budget)
         if self.overlap_allreduce:
             self._side = torch.cuda.Stream(device=tower.flat_params.device)
             self._layer_ranges, self._rest_ranges = self._gradient_ranges()
@@ -125,24 +128,35 @@ class FareTrainer:
         """Hook for the caller's scheduler (utils_AT.py:287-288); constant by default."""
         return self.lr
 
+    def _exchange(self):
+        """Data-parallel average of the accumulated gradients: wait for the slices exchanged while the backward ran, or one
+        blocking all-reduce of the flat buffer."""
+        if not self._distributed:
+            return
+        if self._reduced:                                     # already exchanged slice by slice while the backward ran
+            for w in self._works:
+                w.wait()                                      # stream-level: the next kernels queue behind the collectives
+            self._works, self._reduced = [], False
+        else:
+            dist.all_reduce(self.tower.flat_grads, op=dist.ReduceOp.AVG, group=self.group)
+
+    def _clip_scale(self, grad_scale: float = 1.0) -> float:
+        """torch.nn.utils.clip_grad_norm_(norm_type=2): the factor min(1, max_norm / (total_norm + 1e-6))."""
+        eng, g = self.tower.leaf_engine, self.tower.flat_grads
+        self._norm.zero_()
+        check(eng._lib.leaf_sumsq(eng._h, _ptr(g), g.numel(), _ptr(self._norm), _stream()))
+        total = math.sqrt(float(self._norm.item())) * grad_scale
+        return min(1.0, self.grad_clip_norm / (total + 1e-6))
+
     def optimizer_step(self, grad_scale: float = 1.0):
         """utils_AT.py:338-362 with scaler = None: all-reduce (DDP's job in the reference), clip, AdamW, zero_grad; then the
         engine re-casts its bf16 operand copies from the updated fp32 parameters."""
         t = self.tower
         g, eng = t.flat_grads, t.leaf_engine
-        if self._distributed:
-            if self._reduced:                                 # already exchanged slice by slice while the backward ran
-                for w in self._works:
-                    w.wait()                                  # stream-level: the optimizer kernels queue behind the collectives
-                self._works, self._reduced = [], False
-            else:
-                dist.all_reduce(g, op=dist.ReduceOp.AVG, group=self.group)
+        self._exchange()
         scale = grad_scale
-        if self.grad_clip_norm is not None:                       # torch.nn.utils.clip_grad_norm_, norm_type 2
-            self._norm.zero_()
-            check(eng._lib.leaf_sumsq(eng._h, _ptr(g), g.numel(), _ptr(self._norm), _stream()))
-            total = math.sqrt(float(self._norm.item())) * grad_scale
-            scale *= min(1.0, self.grad_clip_norm / (total + 1e-6))
+        if self.grad_clip_norm is not None:                       # the clip is folded into AdamW's gradient scale
+            scale *= self._clip_scale(grad_scale)
         self.opt_step += 1
         f = ctypes.c_float
         check(eng._lib.leaf_adamw(eng._h, _ptr(t.flat_params), _ptr(g), _ptr(self.exp_avg), _ptr(self.exp_avg_sq), g.numel(),
@@ -160,12 +174,27 @@ class FareTrainer:
         tok = t.tokenizer(adv_texts)                                                       # :312
         feats = t.encode_text(tok, normalize=self.normalize_fare)                          # :317-319 (train mode == eval: no dropout)
         loss = torch.nn.functional.mse_loss(anchors, feats, reduction="none").sum(dim=-1).mean()      # :321-322
-        if self.overlap_allreduce:                           # exchange during the LAST micro-batch's backward only (DDP no_sync)
-            self._hook_armed = (self.micro + 1) % self.accum_freq == 0
+        last = (self.micro + 1) % self.accum_freq == 0
+        # The reference clips the ACCUMULATED gradients after every micro-batch (:356-357), and its DDP wrapper averages them
+        # in every backward; without clipping, one exchange during the last micro-batch's backward gives the same sums.
+        clip_now = self.grad_clip_norm is not None and not last
+        budget = self.overlap_allreduce and (last or clip_now) and self.backward_sm_budget > 0
+        if self.overlap_allreduce:
+            self._hook_armed = last or clip_now
+        if budget:
+            check(t.leaf_engine._lib.leaf_set_sm_budget(t.leaf_engine._h, self.backward_sm_budget))
         (loss / self.accum_freq).backward()                                                # :329-337
+        if budget:
+            check(t.leaf_engine._lib.leaf_set_sm_budget(t.leaf_engine._h, 0))
         if self.overlap_allreduce:
             self._hook_armed = False
         self.micro += 1
-        if self.micro % self.accum_freq == 0:
+        if last:
             self.optimizer_step()
+        elif clip_now:
+            self._exchange()                                  # averaging identical accumulated values again changes nothing
+            s = self._clip_scale()
+            if s < 1.0:
+                eng, g = t.leaf_engine, t.flat_grads
+                check(eng._lib.leaf_scale(eng._h, _ptr(g), g.numel(), ctypes.c_float(s), _stream()))
         return loss.detach(), adv_texts

@@ -186,8 +186,8 @@ def test_fare_trainer_matches_a_torch_loop():
         feats = b.encode_text(b.tokenizer(adv_b))
         loss_b = torch.nn.functional.mse_loss(anchors, feats, reduction="none").sum(dim=-1).mean()
         (loss_b / 2).backward()
+        torch.nn.utils.clip_grad_norm_([p for _, p in named], 0.5, norm_type=2.0)       # after EVERY micro-batch (utils_AT.py:356-357)
         if (i + 1) % 2 == 0:
-            torch.nn.utils.clip_grad_norm_([p for _, p in named], 0.5, norm_type=2.0)
             opt.step()
             opt.zero_grad()
             b.refresh()
