@@ -360,17 +360,34 @@ class LeafEngine:
                                        _ptr(best_feat), _stream()))
         return best, best_feat, loss
 
+    TOPK_MAX = 200 * 1024 // 4         # scores one leaf_topk launch holds in shared memory
+
     def topk(self, score_a: torch.Tensor, k: int, m: int = None, score_b: torch.Tensor = None):
         """Indices (int32 [k]) and values of the k largest of the first m scores; value descending, ties by ascending
-        index. score_b: a second tower's scores of the same candidates, averaged in (utils_attacks.py:498-513)."""
+        index. score_b: a second tower's scores of the same candidates, averaged in (utils_attacks.py:498-513). Longer lists
+        (brute force over a caption of more than ~266 characters: (2 len + 1) * |V| candidates) go through leaf_topk in chunks
+        and one more launch over the chunks' winners - equal values keep their index order through both levels."""
         score_a = score_a.reshape(-1)
         m = score_a.numel() if m is None else int(m)
         if score_b is not None:
             score_b = score_b.reshape(-1)
+        if m > self.TOPK_MAX:
+            idxs, vals = [], []
+            for lo in range(0, m, self.TOPK_MAX):
+                hi = min(m, lo + self.TOPK_MAX)
+                i, v = self.topk(score_a[lo:hi], min(k, hi - lo), score_b=None if score_b is None else score_b[lo:hi])
+                idxs.append(i + lo)
+                vals.append(v)
+            idx_all, val_all = torch.cat(idxs), torch.cat(vals).contiguous()
+            if val_all.numel() > self.TOPK_MAX:
+                raise LeafError(f"top-{k} of {m} scores needs more than two levels")
+            pick, val = self.topk(val_all, k)
+            return idx_all[pick.long()].contiguous(), val
         idx = torch.empty((k,), dtype=torch.int32, device=self.device)
         val = torch.empty((k,), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            check(self._lib.leaf_topk(self._h, _ptr(score_a), _ptr(score_b), m, int(k), _ptr(idx), _ptr(val), _stream()))
+            check(self._lib.leaf_topk(self._h, _ptr(score_a.contiguous()), _ptr(None if score_b is None else score_b.contiguous()), m, int(k),
+                                      _ptr(idx), _ptr(val), _stream()))
         return idx, val
 
     # ---- hooks for tests / bench ---------------------------------------------------------------------------

@@ -34,25 +34,37 @@ def _score_list(eng, eng2, sentence, pos, chr_, anchor, anchor2, objective, vali
     output: no host round trip between the phases). Returns the [groups, per] loss tensor of each tower."""
     groups, per = pos.shape
     dev = eng.device
-    caps_d, off_d = eng.upload_captions([sentence] * groups)
     pos_d = pos if torch.is_tensor(pos) else _to_dev(np.ascontiguousarray(pos, dtype=np.int32), dev)
     chr_d = _to_dev(np.ascontiguousarray(chr_, dtype=np.int32), dev)
     valid_d = None if valid is None else _to_dev(np.ascontiguousarray(valid, dtype=np.uint8), dev)
-    if device_filter:                                                          # constrain=True: the mask never leaves the device
-        valid_d = eng.constrain_mask(caps_d, off_d, groups, per, pos_d, chr_d)
-    eng.reserve(groups * per + groups)
-    tok, ln, base = eng.expand_tokenize(caps_d, off_d, groups, per, pos=pos_d, chr_=chr_d, valid=valid_d)
     norm = objective in ("sim", "dissim")
-    out = []
-    for e, a in ((eng, anchor), (eng2, anchor2)):
-        if e is None:
-            out.append(None)
-            continue
-        e.reserve(groups * per + groups)
-        feats = e.encode_tokens(tok, ln, norm, base, (groups * per, per), trim=True)
-        _, _, loss = e.score(feats, a.expand(groups, -1).contiguous(), groups, per, objective, want_loss=True)
-        out.append(loss)
-    return out + [valid_d]
+    # whole groups per pass, at most MAX_SEQS sequences at once (the workspace is sized for 77 rows per sequence: a brute
+    # force over a 500-character caption is 96 000 candidates; the reference walks its list in batch_size pieces as well)
+    gstep = max(1, MAX_SEQS // (per + 1))
+    losses, losses2, valids = [], [], []
+    for g0 in range(0, groups, gstep):
+        g1 = min(groups, g0 + gstep)
+        ng = g1 - g0
+        caps_d, off_d = eng.upload_captions([sentence] * ng)
+        p_c, c_c = pos_d[g0:g1].contiguous(), chr_d[g0:g1].contiguous()
+        v_c = None if valid_d is None else valid_d[g0:g1].contiguous()
+        if device_filter:                                                      # constrain=True: the mask never leaves the device
+            v_c = eng.constrain_mask(caps_d, off_d, ng, per, p_c, c_c)
+        eng.reserve(ng * per + ng)
+        tok, ln, base = eng.expand_tokenize(caps_d, off_d, ng, per, pos=p_c, chr_=c_c, valid=v_c)
+        for e, a, dst in ((eng, anchor, losses), (eng2, anchor2, losses2)):
+            if e is None:
+                continue
+            e.reserve(ng * per + ng)
+            feats = e.encode_tokens(tok, ln, norm, base, (ng * per, per), trim=True)
+            _, _, loss = e.score(feats, a.expand(ng, -1).contiguous(), ng, per, objective, want_loss=True)
+            dst.append(loss)
+        valids.append(v_c)
+    cat = lambda xs: None if not xs or xs[0] is None else (xs[0] if len(xs) == 1 else torch.cat(xs, dim=0))
+    return [cat(losses), cat(losses2), cat(valids)]
+
+
+MAX_SEQS = 16384
 
 
 def _prep(model, model_2, anchor_features, model_2_anchor_features, objective, V):

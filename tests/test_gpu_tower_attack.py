@@ -280,7 +280,7 @@ def test_topk_kernel():
     from leaf_b200.tower import LeafTextTower
     eng = LeafTextTower.random("tiny", seed=0).leaf_engine
     g = torch.Generator(device="cuda").manual_seed(3)
-    for m_total, m, k in ((1, 1, 1), (97, 96, 10), (5000, 4999, 50), (20000, 19999, 1)):
+    for m_total, m, k in ((1, 1, 1), (97, 96, 10), (5000, 4999, 50), (20000, 19999, 1), (130000, 129999, 1), (130000, 129999, 7)):   # > one launch
         a = torch.randn(m_total, generator=g, device="cuda")
         a[torch.randint(0, m_total, (m_total // 3 + 1,), generator=g, device="cuda")] = 0.25     # plenty of exact ties
         b = torch.randn(m_total, generator=g, device="cuda")
@@ -380,3 +380,29 @@ def test_bigg_width_tower_and_rho_sweep():
         loss_adv = ((feats - anchor) ** 2).sum(-1)
         loss_clean = ((f - anchor) ** 2).sum(-1)
         assert bool((loss_adv >= loss_clean * (1 - LOSS_RTOL)).all()) or rho < 20
+
+
+def test_bruteforce_on_a_long_caption_is_chunked():
+    """attack_text_bruteforce over a 300-character caption: (2*300+1)*96 = 57 696 candidates - more than one leaf_topk launch
+    holds and more sequences than one encode pass takes (eval_attacks.MAX_SEQS). The winner must be the first maximal
+    candidate of the whole list except the never-scored last one (utils_attacks.py:447), found here by scoring every candidate
+    string separately."""
+    from leaf_b200 import attack_text_bruteforce, generate_sentence, synth
+    from leaf_b200.tower import LeafTextTower
+    tower = LeafTextTower.random("tiny", seed=3)
+    eng = tower.leaf_engine
+    S = " ".join(synth.make_captions(8, seed=31))[:300]
+    assert len(S) == 300
+    f0 = tower.encode_text(tower.tokenizer([S]))
+    anchor = (f0 + 0.05 * torch.randn_like(f0)).contiguous()
+    adv, dist_ = attack_text_bruteforce(tower, None, S, anchor.clone(), "cuda", objective="l2")
+    V = synth.V_DEFAULT
+    cands = [generate_sentence(S, z, c) for z in range(2 * len(S) + 1) for c in V]
+    losses = []
+    for s in range(0, len(cands), 8192):
+        f = tower.encode_text(tower.tokenizer(cands[s:s + 8192]))
+        losses.append(((f - anchor) ** 2).sum(-1))
+    loss = torch.cat(losses)[:-1]
+    best = int(loss.argmax())
+    got = cands.index(adv)                                  # first candidate spelling the returned sentence
+    assert dist_ == 1 and got <= best and float(loss[got]) >= float(loss[best]) * (1 - 1e-6), (adv, cands[best], float(loss[got]), float(loss[best]))
