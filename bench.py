@@ -551,6 +551,15 @@ def run_ours(a):
     per_rank = dict(ms_per_step=[round(float(t[0]), 3) for t in per_rank], e2e_ms_per_step=[round(float(t[1]), 3) for t in per_rank],
                     sm_mhz=[int(t[2]) for t in per_rank])
 
+    # the same executed FLOPs against the tensor peak AT THE CLOCK THE BOARD'S POWER CAP ALLOWED during the timed region
+    # (SMs x 8192 dense bf16 FLOP per clock x the median SM clock nvidia-smi reported under load)
+    if clk_sum.get("sm_mhz"):
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        cpeak = sms * 8192 * clk_sum["sm_mhz"] * 1e6 / 1e12
+        roofline["clock_scaled_peak_tflops"] = cpeak
+        roofline["frac_of_clock_scaled_peak"] = achieved / cpeak
+        roofline["clock_scaled_note"] = ("achieved / (SMs x 8192 FLOP/clk x median SM clock under load): what the tensor pipe delivers of what the "
+                                         "power-capped clock allows; ncu's sm__pipe_tensor_cycles_active reads 85-94 % on these GEMMs (profiles/r2_17_ncu_summary.txt)")
     h2d = int(sum(len(c) for c in caps) + 32 + 4 * (B + 1) + 3 * 4 * B * n) * k
     d2h = (2 * 4 * B + 4 + 4) * k
     line = dict(metric=METRIC, value=total_cands / (dev_ms * 1e-3), unit=UNIT, n_gpus=world, steps=a.steps, warmup=a.warmup,

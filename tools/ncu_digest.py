@@ -11,7 +11,9 @@ WANT = [("gpu__time_duration.sum", "duration"), ("sm__cycles_elapsed.avg.per_sec
         ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
         ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput %"), ("lts__t_sector_hit_rate.pct", "L2 hit %"),
         ("l1tex__throughput.avg.pct_of_peak_sustained_active", "L1/TEX throughput %"),
-        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active (realtime) %"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active % of elapsed"),
+        ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__mem_tensor_cycles_active % of elapsed"),
+        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe active (realtime, triage) %"),
         ("sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed", "bf16 tensor ops % of peak"),
         ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
         ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
