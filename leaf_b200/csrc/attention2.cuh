@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(AT2_WARPS * 32, 2) attention2_kernel(const __n
       if (kt == 0) {                                        // nothing accumulated yet: no rescale
         l0 = s0; l1 = s1;
       } else {
-        const float r0 = att_ex2(fmaf(m0, sl2, nm0)), r1 = att_ex2(fmaf(m1, sl2, nm1));
+        // (m - n) * scale, NOT fma(m, scale, -n * scale): a key tile that is fully masked for a row must rescale it by exactly 1
+        // (which tiles a row meets beyond its own keys depends on the packing; results must not)
+        const float r0 = att_ex2((m0 - n0) * sl2), r1 = att_ex2((m1 - n1) * sl2);
         l0 = fmaf(l0, r0, s0);
         l1 = fmaf(l1, r1, s1);
 #pragma unroll
