@@ -39,7 +39,7 @@ typedef struct leaf_engine* leaf_handle_t;
 enum { LEAF_ACT_GELU_ERF = 0, LEAF_ACT_QUICK_GELU = 1 };
 enum { LEAF_OBJ_L2 = 0, LEAF_OBJ_NEGL2 = 1, LEAF_OBJ_SIM = 2, LEAF_OBJ_DISSIM = 3 };
 enum { LEAF_CTX = 77, LEAF_SOT = 49406, LEAF_EOT = 49407, LEAF_VOCAB = 49408, LEAF_N_MERGES = 48894 };
-enum { LEAF_MAX_CAPTION_BYTES = 1000 };
+enum { LEAF_MAX_CAPTION_BYTES = 1000, LEAF_MAX_CAPTION_BYTES_LONG = 4072 };
 
 /* Text-tower shape: src/open_clip/model_configs/ViT-{L,H,g,bigG}-14.json "text_cfg" + "embed_dim". */
 typedef struct {
@@ -118,6 +118,10 @@ int leaf_expand_tokenize(leaf_handle_t h, const uint8_t* caps, const int32_t* ca
  * 1 = transformers' CLIPTokenizer as the reference's HF evaluation path wraps it (utils_attacks.py:67-71,
  * eval_textfare.py:127): same BPE, no html.unescape, special tokens spelled <|startoftext|> / <|endoftext|>. */
 int leaf_set_tokenizer_mode(leaf_handle_t h, int32_t mode);
+/* Largest caption (UTF-8 bytes) the next leaf_expand_tokenize calls will see. Up to LEAF_MAX_CAPTION_BYTES (the default) the
+ * kernel runs four candidates per CTA; beyond, up to LEAF_MAX_CAPTION_BYTES_LONG, its long-text variant (one per CTA) is used.
+ * The reference's tokenizer takes text of any length (tokenizer.py:226-265); longer captions are flagged (status bit 4). */
+int leaf_set_max_caption_bytes(leaf_handle_t h, int32_t bytes);
 
 /* ---- the `--constrain` filter on the device ---------------------------------------------------------
  * Replaces valid_sentence_batched (utils_attacks.py:110-143; applied at :321-325, :360-364, :478-481, :532-537):

@@ -39,6 +39,7 @@ SIGNATURES = {
     "leaf_expand_tokenize": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "leaf_set_tokenizer_mode": (c_int, [c_void_p, c_int]),
+    "leaf_set_max_caption_bytes": (c_int, [c_void_p, c_int]),
     "leaf_load_words": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int]),
     "leaf_constrain_mask": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_void_p]),

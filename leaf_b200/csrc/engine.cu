@@ -82,6 +82,7 @@ struct leaf_engine {
   // K1 tables
   bool bpe_loaded = false;
   bool hf_tokenizer = false;          // leaf_set_tokenizer_mode
+  int max_caption_bytes = LEAF_MAX_CAPTION_BYTES;   // leaf_set_max_caption_bytes
   std::vector<void*> table_allocs;
   K1Tables tables{};
   // --constrain filter: hash sets of the word list and of Punkt abbreviation types
@@ -483,8 +484,12 @@ extern "C" int leaf_expand_tokenize(leaf_handle_t e, const uint8_t* caps, const 
   if (n > 0 && (!pos || !chr)) return fail(LEAF_ERR_INVALID, "pos/chr required when n > 0");
   K1Args a{caps, cap_off, B, n, pos, chr, sel, valid, tok_out, len_out, base_out, status_out, e->hf_tokenizer ? 1 : 0};
   const long R = static_cast<long>(B) * (n > 0 ? n : 1) + (n > 0 ? B : 0);
-  const int grid = static_cast<int>((R + K1_WARPS_PER_CTA - 1) / K1_WARPS_PER_CTA);
-  k1_expand_tokenize_kernel<<<grid, K1_WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(e->tables, a);
+  if (e->max_caption_bytes > LEAF_MAX_CAPTION_BYTES) {        // long captions: one warp per CTA with 4 KB text buffers
+    k1_expand_tokenize_kernel<K1_LONG_TEXT, 1><<<static_cast<int>(R), 32, 0, static_cast<cudaStream_t>(stream)>>>(e->tables, a);
+  } else {
+    const int grid = static_cast<int>((R + K1_WARPS_PER_CTA - 1) / K1_WARPS_PER_CTA);
+    k1_expand_tokenize_kernel<K1_MAX_TEXT, K1_WARPS_PER_CTA><<<grid, K1_WARPS_PER_CTA * 32, 0, static_cast<cudaStream_t>(stream)>>>(e->tables, a);
+  }
   e->launches++;
   CK(cudaGetLastError());
   return LEAF_OK;
@@ -1065,6 +1070,14 @@ extern "C" int leaf_constrain_mask(leaf_handle_t e, const uint8_t* caps, const i
   constrain_valid_kernel<<<(B * n + 255) / 256, 256, 0, st>>>(cnt, B, n, valid_out);
   e->launches += 2;
   CK(cudaGetLastError());
+  return LEAF_OK;
+}
+
+// Captions longer than LEAF_MAX_CAPTION_BYTES (up to LEAF_MAX_CAPTION_BYTES_LONG) switch leaf_expand_tokenize to its
+// long-text variant (one warp per CTA, 4 KB text buffers: ~4 x slower on a kernel that takes 0.15 ms per 6 528 rows).
+extern "C" int leaf_set_max_caption_bytes(leaf_handle_t e, int32_t bytes) {
+  if (!e || bytes <= 0 || bytes > LEAF_MAX_CAPTION_BYTES_LONG) return fail(LEAF_ERR_INVALID, "caption limit %d (max %d)", bytes, LEAF_MAX_CAPTION_BYTES_LONG);
+  e->max_caption_bytes = bytes;
   return LEAF_OK;
 }
 

@@ -14,7 +14,8 @@
 
 namespace leaf {
 
-constexpr int K1_WARPS_PER_CTA = 4;
+constexpr int K1_WARPS_PER_CTA = 4;          // default variant: captions up to 1000 bytes, 4 warps x 11 KB of scratch per CTA
+constexpr int K1_LONG_TEXT = 4096;           // long variant: captions up to 4072 bytes, one warp (45 KB of scratch) per CTA
 
 struct K1Args {
   const uint8_t* caps;
@@ -31,29 +32,30 @@ struct K1Args {
   int hf_mode;            // 1: HF CLIPTokenizer semantics (leaf_set_tokenizer_mode)
 };
 
-__global__ void __launch_bounds__(K1_WARPS_PER_CTA * 32) k1_expand_tokenize_kernel(const K1Tables T, const K1Args a) {
-  __shared__ __align__(16) uint8_t s_src[K1_WARPS_PER_CTA][K1_MAX_TEXT];
-  __shared__ __align__(16) uint8_t s_a[K1_WARPS_PER_CTA][K1_MAX_TEXT];
-  __shared__ __align__(16) uint8_t s_b[K1_WARPS_PER_CTA][K1_MAX_TEXT];
-  __shared__ uint16_t s_sym[K1_WARPS_PER_CTA][2 * K1_MAX_TEXT];
-  __shared__ uint16_t s_rk[K1_WARPS_PER_CTA][2 * K1_MAX_TEXT];
-  __shared__ uint16_t s_ps[K1_WARPS_PER_CTA][K1_MAX_PIECES];
-  __shared__ uint16_t s_pl[K1_WARPS_PER_CTA][K1_MAX_PIECES];
-  __shared__ int32_t s_row[K1_WARPS_PER_CTA][K1_CTX + 3];
-  __shared__ int s_meta[K1_WARPS_PER_CTA][4];
+template <int MAXT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k1_expand_tokenize_kernel(const K1Tables T, const K1Args a) {
+  __shared__ __align__(16) uint8_t s_src[WARPS][MAXT];
+  __shared__ __align__(16) uint8_t s_a[WARPS][MAXT];
+  __shared__ __align__(16) uint8_t s_b[WARPS][MAXT];
+  __shared__ uint16_t s_sym[WARPS][2 * MAXT];
+  __shared__ uint16_t s_rk[WARPS][2 * MAXT];
+  __shared__ uint16_t s_ps[WARPS][K1_MAX_PIECES];
+  __shared__ uint16_t s_pl[WARPS][K1_MAX_PIECES];
+  __shared__ int32_t s_row[WARPS][K1_CTX + 3];
+  __shared__ int s_meta[WARPS][4];
 
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per = a.n > 0 ? a.n : 1;
   const int n_cand = a.B * per;
   const int R = n_cand + (a.n > 0 ? a.B : 0);          // candidates, then (n > 0) the B unedited captions
-  const int r = blockIdx.x * K1_WARPS_PER_CTA + w;
+  const int r = blockIdx.x * WARPS + w;
   if (r >= R) return;
   const bool is_base = r >= n_cand;
   const int b = is_base ? r - n_cand : r / per;
   const int off = a.cap_off[b];
   int len = a.cap_off[b + 1] - off;
   int flags = 0;
-  if (len > 1000) { flags |= K1_FLAG_TOO_LONG; len = 0; }
+  if (len > MAXT - 24) { flags |= K1_FLAG_TOO_LONG; len = 0; }      // one inserted character and the 16-byte load tail fit
   const uint8_t* src = a.caps + off;
   if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     for (int i = lane * 16; i < len; i += 32 * 16)        // may read up to 15 bytes past the caption: callers pad

@@ -25,7 +25,8 @@ MERGES_BIN = os.path.join(HERE, "data", "clip_bpe_merges.bin")
 CONTEXT_LENGTH = 77
 OBJECTIVES = {"l2": 0, "negl2": 1, "sim": 2, "dissim": 3}
 STATUS_ENTITY_DOMAIN, STATUS_NON_ASCII, STATUS_TOO_LONG = 1, 2, 4
-MAX_CAPTION_BYTES = 1000
+MAX_CAPTION_BYTES = 1000            # the tokenizer kernel's default variant; up to MAX_CAPTION_BYTES_LONG with its long-text variant
+MAX_CAPTION_BYTES_LONG = 4072
 
 
 def _ptr(t):
@@ -113,6 +114,7 @@ class LeafEngine:
         self._status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.has_words = False
         self.max_seqs = 0
+        self._caption_limit = MAX_CAPTION_BYTES
         if max_seqs:
             self.reserve(max_seqs)
 
@@ -178,8 +180,8 @@ class LeafEngine:
                 bad = next(c for c in s if ord(c) > 0xFF)
                 raise LeafError(f"caption outside the tokenizer kernel's domain (code points <= U+00FF): U+{ord(bad):04X} in {s!r}")
             b = s.encode("utf-8")
-            if len(b) > MAX_CAPTION_BYTES:
-                raise LeafError(f"caption longer than {MAX_CAPTION_BYTES} bytes")
+            if len(b) > MAX_CAPTION_BYTES_LONG:
+                raise LeafError(f"caption longer than {MAX_CAPTION_BYTES_LONG} bytes")
             blobs.append(b)
         off = np.zeros(len(blobs) + 1, dtype=np.int32)
         off[1:] = np.cumsum([len(b) for b in blobs])
@@ -188,6 +190,10 @@ class LeafEngine:
 
     def upload_captions(self, sentences):
         data, off = self.pack_captions(sentences)
+        longest = int(np.diff(off).max()) if len(off) > 1 else 0
+        if longest > self._caption_limit:                   # sticky: the long-text kernel variant handles short captions too
+            self._caption_limit = MAX_CAPTION_BYTES_LONG
+            check(self._lib.leaf_set_max_caption_bytes(self._h, MAX_CAPTION_BYTES_LONG))
         d = torch.from_numpy(data.copy()).pin_memory().to(self.device, non_blocking=True)
         o = torch.from_numpy(off).pin_memory().to(self.device, non_blocking=True)
         return d, o

@@ -26,8 +26,9 @@ extern "C" int k1h_expand_tokenize(const uint8_t* caps, const int32_t* cap_off, 
                                    const int32_t* chr, const int32_t* sel, const uint8_t* valid, int32_t* tok_out,
                                    int32_t* len_out) {
   K1Tables T = k1_host_tables(g_tab.data());
-  std::vector<uint8_t> a(K1_MAX_TEXT), b(K1_MAX_TEXT);
-  std::vector<uint16_t> sym(2 * K1_MAX_TEXT), rk(2 * K1_MAX_TEXT), ps(K1_MAX_PIECES), pl(K1_MAX_PIECES);
+  constexpr int MAXT = 4096;                 // the long-text variant's buffers (k1_tokenize.cuh: K1_LONG_TEXT)
+  std::vector<uint8_t> a(MAXT), b(MAXT);
+  std::vector<uint16_t> sym(2 * MAXT), rk(2 * MAXT), ps(K1_MAX_PIECES), pl(K1_MAX_PIECES);
   K1Scratch S{a.data(), b.data(), sym.data(), rk.data(), ps.data(), pl.data(), 0, 0};
   int flags = 0;
   const int per = n > 0 ? n : 1;
@@ -35,7 +36,7 @@ extern "C" int k1h_expand_tokenize(const uint8_t* caps, const int32_t* cap_off, 
     const int bb = r / per, j = r % per;
     const uint8_t* src = caps + cap_off[bb];
     int len = cap_off[bb + 1] - cap_off[bb];
-    if (len > 1000) { flags |= K1_FLAG_TOO_LONG; len = 0; }
+    if (len > MAXT - 24) { flags |= K1_FLAG_TOO_LONG; len = 0; }
     bool edit = n > 0 && (!valid || valid[r]);
     int z = 0, c = -1;
     if (n > 0) {

@@ -287,6 +287,31 @@ def test_k1_latin1_utf8_captions(eng, golden_dir):
     eng._status.zero_()
 
 
+def test_k1_long_captions(eng):
+    """Captions of 1000-4072 bytes switch the tokenizer kernel to its long-text variant (sticky per engine); rows equal the oracle's
+    and the CPU-compiled core's, the attack runs on them, and longer captions raise."""
+    from leaf_b200 import LeafError, attack_text_leaf, synth
+    from leaf_b200.tower import LeafTextTower
+    from oracle import leaf_oracle as O
+    from tests import k1_harness as H
+    e = LeafTextTower.random("tiny", seed=2).leaf_engine                     # its own engine: the switch is sticky
+    caps = [" ".join(synth.make_captions(40, seed=s))[:L] for s, L in ((1, 1500), (2, 2600), (3, 4072))] + ["short one", "caf\u00e9 " * 500]
+    assert torch.equal(e.tokenize(caps).cpu(), O.OracleTokenizer()(caps))
+    rng = np.random.RandomState(0)
+    n = 16
+    pos = np.stack([rng.randint(0, 2 * len(S) + 1, size=n) for S in caps]).astype(np.int32)
+    chr_ = np.array(synth.V_DEFAULT, dtype=np.int32)[rng.randint(0, 96, size=(len(caps), n))]
+    tok, ln = _k1(e, caps, n, pos, chr_)
+    htok, hln, _ = H.expand_tokenize(caps, n, pos, chr_)
+    assert (tok == htok).all() and (ln == hln).all()
+    anchor = e.encode_tokens(e.tokenize(caps)) + 0.1
+    np.random.seed(1)
+    feats, adv = attack_text_leaf(e, None, caps, anchor, "cuda", n=8, k=1)
+    assert torch.equal(e.encode_tokens(e.tokenize(adv)), feats) and all(abs(len(a) - len(c)) <= 1 for a, c in zip(adv, caps))
+    with pytest.raises(LeafError, match="longer"):
+        e.tokenize(["z" * 4073])
+
+
 def test_k1_candidates_bit_exact(eng):
     from leaf_b200 import synth
     from oracle import leaf_oracle as O

@@ -185,3 +185,27 @@ def test_latin1_utf8_captions_golden(golden_dir):
     t, l = np.zeros((1, 77), dtype=np.int32), np.zeros(1, dtype=np.int32)
     p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
     assert L.k1h_expand_tokenize(p(data), p(off), 1, 0, None, None, None, None, p(t), p(l)) & 2
+
+
+def test_long_captions_up_to_4072_bytes():
+    """Captions beyond the default variant's 1000 bytes (the reference's tokenizer takes any length, tokenizer.py:226-265): the
+    long-text buffers of the kernel's second variant, against the oracle tokenizer, with edits anywhere in the text - most of
+    them behind the 77-token window, where the row must equal the caption's; longer than 4072 bytes is flagged."""
+    rng = random.Random(3)
+    otok = O.OracleTokenizer()
+    caps = [" ".join(synth.make_captions(40, seed=s, kind="typical"))[:L] for s, L in ((1, 1500), (2, 2600), (3, 4072))]
+    caps += ["x" * 4072, ("ab " * 1400)[:4000], "caf\u00e9 " * 500, "a" + " " * 3000 + "b &amp; c"]
+    assert max(len(c.encode("utf-8")) for c in caps) == 4072
+    n = 24
+    pos = np.array([[rng.randint(0, 2 * len(S)) for _ in range(n)] for S in caps], dtype=np.int32)
+    pos[:, :4] = [[0, 1, 40, 90]] * len(caps)                                # some inside the window
+    chr_ = np.array([[V[rng.randrange(len(V))] for _ in range(n)] for _ in caps], dtype=np.int32)
+    tok, ln, flags = H.expand_tokenize(caps, n=n, pos=pos, chr_=chr_)
+    assert flags == 0
+    strings = [O.edit_sentence(S, int(pos[b, j]), int(chr_[b, j])) for b, S in enumerate(caps) for j in range(n)]
+    want = otok(strings).numpy()
+    assert (tok == want).all()
+    base, _, _ = H.expand_tokenize(caps)
+    assert (base == otok(caps).numpy()).all()
+    _, _, fl = H.expand_tokenize(["y" * 4073])
+    assert fl & 4
