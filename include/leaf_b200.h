@@ -175,8 +175,9 @@ int leaf_topk(leaf_handle_t h, const float* score_a, const float* score_b, int32
  * Replaces model.encode_text(adv_tokens) under autograd and loss.backward() of utils_AT.py:317-337 (the loss itself,
  * mse(...).sum(-1).mean() on [B,E], stays a two-line torch expression on top of feat_out / dfeat).
  * leaf_train_reserve sizes the activation store (and makes the [in,out] bf16 weight copies the dgrad products need);
- * leaf_forward_train computes feat_out [N,E] fp32 and keeps every layer's activations (it synchronises the stream once
- * to learn the packed row count); leaf_backward consumes dfeat [N,E] fp32 and ACCUMULATES (+=) the parameter
+ * leaf_forward_train computes feat_out [N,E] fp32 and keeps every layer's activations. The packed row count sizes the
+ * weight-gradient contractions on the host: pass rows_hint = sum(len) and max_len_hint >= max(len) when the host knows them
+ * (checked on the device: a wrong hint traps) and nothing synchronises; with 0 / 0 the stream is synchronised once to learn them; leaf_backward consumes dfeat [N,E] fp32 and ACCUMULATES (+=) the parameter
  * gradients into the fp32 device buffers named by `grads` (same struct and layouts as leaf_bind_weights; a NULL
  * pointer marks a frozen parameter). bf16 operands, fp32 accumulation, fp32 LayerNorm/softmax/activation math.
  * ONE forward, ONE backward: the engine keeps a single activation store. Every leaf_forward_train gets a generation
@@ -186,7 +187,7 @@ int leaf_topk(leaf_handle_t h, const float* score_a, const float* score_b, int32
  * LEAF_ERR_INVALID when dfeat_rows is not the N of that forward. The store is consumed by a successful backward. */
 int leaf_train_reserve(leaf_handle_t h, int32_t max_seqs);
 int leaf_forward_train(leaf_handle_t h, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out,
-                       int64_t* generation_out, void* stream);
+                       int32_t rows_hint, int32_t max_len_hint, int64_t* generation_out, void* stream);
 int leaf_backward(leaf_handle_t h, int64_t generation, const float* dfeat, int32_t dfeat_rows, const leaf_weight_ptrs_t* grads,
                   void* stream);
 

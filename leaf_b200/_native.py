@@ -47,7 +47,7 @@ SIGNATURES = {
     "leaf_score": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "leaf_topk": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "leaf_train_reserve": (c_int, [c_void_p, c_int]),
-    "leaf_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, ctypes.POINTER(c_i64), c_void_p]),
+    "leaf_forward_train": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, ctypes.POINTER(c_i64), c_void_p]),
     "leaf_backward": (c_int, [c_void_p, c_i64, c_void_p, c_int, ctypes.POINTER(LeafWeightPtrs), c_void_p]),
     "leaf_set_backward_hook": (c_int, [c_void_p, c_void_p, c_void_p]),
     "leaf_set_sm_budget": (c_int, [c_void_p, c_int]),

@@ -802,8 +802,13 @@ static int launch_ew(leaf_engine* e, size_t n) {      // grid for the grid-strid
   return static_cast<int>(b < cap ? (b ? b : 1) : cap);
 }
 
+// traps (a CUDA error at the next synchronisation) when the caller's row-count hints are not what the device computed
+__global__ void check_train_hints_kernel(const int* __restrict__ total_rows, int rows, int max_len) {
+  if (total_rows[0] != rows || total_rows[1] > max_len) __trap();
+}
+
 extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int32_t* len, int32_t N, float* feat_out,
-                                  int64_t* generation_out, void* stream) {
+                                  int32_t rows_hint, int32_t max_len_hint, int64_t* generation_out, void* stream) {
   if (!e || !tok || !len || !feat_out || N <= 0) return fail(LEAF_ERR_INVALID, "bad argument");
   if (!e->bound) return fail(LEAF_ERR_STATE, "weights not bound");
   if (N > e->tw.max_seqs) return fail(LEAF_ERR_STATE, "training workspace reserved for %d sequences, need %d (leaf_train_reserve)", e->tw.max_seqs, N);
@@ -818,9 +823,14 @@ extern "C" int leaf_forward_train(leaf_handle_t e, const int32_t* tok, const int
   scan_lengths_kernel<<<1, 1024, 0, st>>>(t.own_len, N, t.cu, t.total_rows, t.total_rows + 1);
   meta_kernel<<<(N + 255) / 256, 256, 0, st>>>(t.cu, t.pfx, nullptr, nullptr, N, t.meta, t.eos_row);
   e->launches += 3;
-  int mt[2] = {0, 0};
-  CK(cudaMemcpyAsync(mt, t.total_rows, 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));                       // packed row count (sizes the wgrad contractions) + longest sequence
+  int mt[2] = {rows_hint, max_len_hint};
+  if (rows_hint > 0 && max_len_hint > 0) {             // the caller knows the lengths (e.g. from the tokenizer's status read): no sync
+    check_train_hints_kernel<<<1, 1, 0, st>>>(t.total_rows, rows_hint, max_len_hint);
+    e->launches++;
+  } else {
+    CK(cudaMemcpyAsync(mt, t.total_rows, 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));                     // packed row count (sizes the wgrad contractions) + longest sequence
+  }
   const int M = mt[0];
   if (M <= 0 || M > t.rows_cap || mt[1] <= 0 || mt[1] > LEAF_CTX) return fail(LEAF_ERR_STATE, "bad packed row count %d / length %d", M, mt[1]);
   t.N = N; t.M = M; t.T = mt[1];

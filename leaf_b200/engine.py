@@ -294,12 +294,19 @@ class LeafEngine:
         rows[:, :L] = torch.where(keep, tok.to(torch.int32), torch.zeros_like(tok, dtype=torch.int32))
         return self.encode_tokens(rows, ln, normalize)
 
-    def tokenize(self, texts, check=True) -> torch.Tensor:
-        """SimpleTokenizer.__call__ (tokenizer.py:226-265): int64 [N,77] on the engine's device."""
+    def tokenize(self, texts, check=True, with_lengths=False):
+        """SimpleTokenizer.__call__ (tokenizer.py:226-265): int64 [N,77] on the engine's device. with_lengths: also the pooled
+        lengths argmax(ids) + 1 as a host list - they ride on the status read, so knowing them costs no extra synchronisation
+        (forward_train takes them as hints and then does not synchronise either)."""
         if isinstance(texts, str):
             texts = [texts]
         d, o = self.upload_captions(texts)
-        tok, _, _ = self.expand_tokenize(d, o, len(texts), 0)
+        tok, ln, _ = self.expand_tokenize(d, o, len(texts), 0)
+        if with_lengths:
+            both = torch.cat([self._status, ln]).cpu().tolist()              # ONE device -> host read: status flags + lengths
+            if both[0]:
+                self.check_status()
+            return tok.long(), both[1:]
         if check:
             self.check_status()
         return tok.long()
@@ -326,8 +333,9 @@ class LeafEngine:
         return out
 
     # ---- K4 ----------------------------------------------------------------------------------------------
-    def forward_train(self, tok: torch.Tensor, lengths: torch.Tensor = None) -> torch.Tensor:
-        """encode_text in train mode (utils_AT.py:317-319): same features, every layer's activations are kept."""
+    def forward_train(self, tok: torch.Tensor, lengths: torch.Tensor = None, host_lengths=None) -> torch.Tensor:
+        """encode_text in train mode (utils_AT.py:317-319): same features, every layer's activations are kept. host_lengths: the
+        rows' pooled lengths as a host list (tokenize(..., with_lengths=True)) - with them the call does not synchronise."""
         tok = tok.to(torch.int32).contiguous()
         N = tok.shape[0]
         if lengths is None:
@@ -336,7 +344,9 @@ class LeafEngine:
         with torch.cuda.device(self.device):
             check(self._lib.leaf_train_reserve(self._h, N))
             gen = ctypes.c_int64(0)
-            check(self._lib.leaf_forward_train(self._h, _ptr(tok), _ptr(lengths.contiguous()), N, _ptr(out), ctypes.byref(gen), _stream()))
+            rows, longest = (sum(host_lengths), max(host_lengths)) if host_lengths is not None and len(host_lengths) == N else (0, 0)
+            check(self._lib.leaf_forward_train(self._h, _ptr(tok), _ptr(lengths.contiguous()), N, _ptr(out), int(rows), int(longest),
+                                               ctypes.byref(gen), _stream()))
         self.last_generation = int(gen.value)
         return out
 

@@ -171,8 +171,8 @@ class FareTrainer:
         t = self.tower
         anchors = self.anchors(texts)
         adv_texts = self.attack(texts, anchors.clone())
-        tok = t.tokenizer(adv_texts)                                                       # :312
-        feats = t.encode_text(tok, normalize=self.normalize_fare)                          # :317-319 (train mode == eval: no dropout)
+        tok, lens = t.tokenizer(adv_texts, with_lengths=True)                              # :312 (lengths ride on the status read)
+        feats = t.encode_text(tok, normalize=self.normalize_fare, host_lengths=lens)       # :317-319 (train mode == eval: no dropout)
         loss = torch.nn.functional.mse_loss(anchors, feats, reduction="none").sum(dim=-1).mean()      # :321-322
         last = (self.micro + 1) % self.accum_freq == 0
         # The reference clips the ACCUMULATED gradients after every micro-batch (:356-357), and its DDP wrapper averages them

@@ -34,7 +34,8 @@ class _EncodeTextTrain(torch.autograd.Function):
     @staticmethod
     def forward(ctx, tower, tok, *params):
         ctx.tower = tower
-        out = tower.leaf_engine.forward_train(tok)
+        hint, tower._host_lengths = tower._host_lengths, None                 # one-shot: set by encode_text(..., host_lengths=)
+        out = tower.leaf_engine.forward_train(tok, host_lengths=hint)
         ctx.generation = tower.leaf_engine.last_generation
         return out
 
@@ -135,6 +136,7 @@ class LeafTextTower(torch.nn.Module):
             if no_weight_decay(k, v.dim()):
                 self.n_nodecay = off
         self.heads, self.quick_gelu = heads, quick_gelu
+        self._host_lengths = None
         self.leaf_engine = LeafEngine(self.open_clip_state_dict(), heads=heads, quick_gelu=quick_gelu)
 
     @classmethod
@@ -228,8 +230,8 @@ class LeafTextTower(torch.nn.Module):
         """Call after the parameters changed (optimizer step)."""
         self.leaf_engine.refresh_weights()
 
-    def tokenizer(self, texts):
-        return self.leaf_engine.tokenize(texts)
+    def tokenizer(self, texts, with_lengths=False):
+        return self.leaf_engine.tokenize(texts, with_lengths=with_lengths)
 
     def trainable(self, on: bool = True):
         """Mark the tower's parameters as requiring gradients (the attacked tower in train_AT_text_only.py)."""
@@ -237,12 +239,14 @@ class LeafTextTower(torch.nn.Module):
             p.requires_grad_(on)
         return self
 
-    def encode_text(self, text, normalize: bool = False):
-        """model.py:269-284. Under torch.no_grad() (the attack, utils_AT.py:295) this is the inference path; with
+    def encode_text(self, text, normalize: bool = False, host_lengths=None):
+        """model.py:269-284. host_lengths (training path only): the rows' pooled lengths as a host list, from
+        tokenizer(texts, with_lengths=True) - the train-mode forward then needs no stream synchronisation. Under torch.no_grad() (the attack, utils_AT.py:295) this is the inference path; with
         gradients enabled and trainable parameters (utils_AT.py:317-319) the forward keeps its activations and
         loss.backward() runs the engine's backward. Call refresh() after optimizer.step()."""
         params = [p for _, p in self.named_tower_parameters()]
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            self._host_lengths = host_lengths
             f = _EncodeTextTrain.apply(self, text, *params)
             return torch.nn.functional.normalize(f, dim=-1) if normalize else f
         with torch.no_grad():

@@ -91,6 +91,28 @@ def test_one_forward_one_backward_is_enforced():
     assert not torch.equal(tower.flat_grads, g1)
 
 
+def test_train_forward_with_host_lengths_does_not_change_anything():
+    """tokenizer(..., with_lengths=True) returns the pooled lengths with its status read; forward_train(host_lengths=...) then
+    skips its stream synchronisation (the packed row count sizes the weight-gradient contractions on the host). Same features,
+    same gradients as the synchronising path."""
+    from leaf_b200 import synth
+    from leaf_b200.tower import LeafTextTower
+    tower = LeafTextTower.random("small", seed=2).trainable()
+    eng = tower.leaf_engine
+    caps = synth.make_captions(9, seed=3) + ["", "a"]
+    tok, lens = tower.tokenizer(caps, with_lengths=True)
+    assert lens == (tok.argmax(dim=-1) + 1).cpu().tolist() and torch.equal(tok, tower.tokenizer(caps))
+    grads = []
+    for hint in (None, lens):
+        tower.zero_grad()
+        f = tower.encode_text(tok, host_lengths=hint)
+        f.square().sum().backward()
+        grads.append((f.detach().clone(), tower.flat_grads.clone()))
+    assert torch.equal(grads[0][0], grads[1][0])
+    # weight gradients of the 16-48-tile shapes are split-K sums (atomic order): equal to rounding, not to the bit
+    assert ((grads[0][1] - grads[1][1]).norm() / grads[0][1].norm()).item() < 1e-5
+
+
 def test_backward_hf_layout():
     from leaf_b200 import synth
     from leaf_b200.engine import LeafEngine
