@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
                                                             int rows_max, const int* __restrict__ gather, int W,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             float eps, __nv_bfloat16* __restrict__ y,
-                                                            const __nv_bfloat16* __restrict__ delta = nullptr) {
+                                                            const __nv_bfloat16* __restrict__ delta = nullptr,
+                                                            __nv_bfloat16* __restrict__ y_lo = nullptr) {
   const int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -226,6 +227,15 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
       out[lane + 32 * i] = pk;
+      if (y_lo) {                                // what the bf16 rounding dropped, as a second bf16 operand (final projection)
+        const float2 l = __bfloat1622float2(lo), h = __bfloat1622float2(hi);
+        __nv_bfloat162 lo2 = __floats2bfloat162_rn((v[i].x - mean) * rstd * g.x + b.x - l.x, (v[i].y - mean) * rstd * g.y + b.y - l.y);
+        __nv_bfloat162 hi2 = __floats2bfloat162_rn((v[i].z - mean) * rstd * g.z + b.z - h.x, (v[i].w - mean) * rstd * g.w + b.w - h.y);
+        uint2 pk2;
+        pk2.x = *reinterpret_cast<uint32_t*>(&lo2);
+        pk2.y = *reinterpret_cast<uint32_t*>(&hi2);
+        reinterpret_cast<uint2*>(y_lo + static_cast<size_t>(r) * W)[lane + 32 * i] = pk2;
+      }
     }
   }
 }
@@ -564,11 +574,14 @@ __global__ void __launch_bounds__(1024) topk_kernel(const float* __restrict__ a,
 }
 
 // fp32 -> bf16 cast (weight refresh), optional transpose for text_projection [W,E] -> [E,W]
-__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
+// residual = 1: dst = bf16(src - float(bf16(src))), the part of src its bf16 copy dropped (second operand of the final projection)
+__device__ __forceinline__ float bf16_residual(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n, int residual = 0) {
   size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x * 4;
   for (; i + 3 < n; i += stride) {
-    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    float4 v = *reinterpret_cast<const float4*>(src + i);
+    if (residual) { v.x = bf16_residual(v.x); v.y = bf16_residual(v.y); v.z = bf16_residual(v.z); v.w = bf16_residual(v.w); }
     __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&lo);
@@ -577,12 +590,13 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   }
 }
 __global__ void cast_bf16_transpose_kernel(const float* __restrict__ src /*[R,C]*/, __nv_bfloat16* __restrict__ dst /*[C,R]*/,
-                                           int R, int C) {
+                                           int R, int C, int residual = 0) {
   __shared__ float tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (r < R && c < C) ? src[static_cast<size_t>(r) * C + c] : 0.f;
+    const float v = (r < R && c < C) ? src[static_cast<size_t>(r) * C + c] : 0.f;
+    tile[i][threadIdx.x] = residual ? bf16_residual(v) : v;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
