@@ -61,10 +61,16 @@ for overlap in (False, True):
           f"across ranks after the update: {same_params}, moved: {not torch.equal(flat, state0)}", flush=True)
     ok &= same_params and tr.opt_step == 1 and not torch.equal(flat, state0)
     del tr
-diff = (outs[True] - outs[False]).abs().max().item()
-upd = (outs[False] - state0).abs().max().item()
-print(f"rank {rank}: overlapped vs blocking exchange: max |difference| of the updated parameters {diff:.3e} (update size {upd:.3e})", flush=True)
-ok &= diff <= 1e-2 * upd + 1e-12
+# The weight gradients of the 16-48-tile shapes are split-K sums and the bias / LayerNorm gradients atomic sums (run-to-run order),
+# and the first AdamW step turns every gradient into +-lr whatever its size, so single near-zero gradients may move by a few
+# percent of lr between ANY two runs; what must agree is the update as a whole.
+d = outs[True] - outs[False]
+u = outs[False] - state0
+rel = (d.norm() / u.norm()).item()
+frac = (d.abs() > 1e-2 * u.abs().max()).float().mean().item()
+print(f"rank {rank}: overlapped vs blocking exchange: |update difference| / |update| = {rel:.3e}, max |difference| {d.abs().max().item():.3e} "
+      f"(update size {u.abs().max().item():.3e}), elements differing by more than 1 % of it: {frac:.2e}", flush=True)
+ok &= rel <= 1e-3 and frac <= 1e-4
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
