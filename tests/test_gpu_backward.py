@@ -216,8 +216,15 @@ def test_fare_trainer_matches_a_torch_loop():
         assert adv_a == adv_b, i
         assert torch.allclose(loss_a, loss_b.detach(), rtol=1e-5), i
     assert tr.opt_step == 1 and float(a.flat_grads.abs().max()) == 0.0
+    # AdamW turns every gradient into a step of ~lr whatever its size, and the small gradients are atomic / split-K sums whose
+    # order varies run to run: a near-zero gradient may step the other way. So: the update as a whole must agree, and all
+    # but a vanishing share of the elements to the usual tolerance.
+    sd0 = {k: v.cuda() for k, v in sd.items()}
     for (k, pa), (_, pb) in zip(a.named_tower_parameters(), named):
-        assert torch.allclose(pa, pb, rtol=1e-4, atol=1e-6), (k, (pa - pb).abs().max().item())
+        upd = (pb - sd0[k]).norm().clamp_min(1e-12)
+        assert ((pa - pb).norm() / upd).item() < 2e-2, (k, ((pa - pb).norm() / upd).item())
+        bad = ((pa - pb).abs() > 1e-6 + 1e-4 * pb.abs()).float().mean().item()
+        assert bad < 1e-3, (k, bad, (pa - pb).abs().max().item())
     assert not torch.equal(a.flat_params, LeafTextTower(sd, heads=cfg.heads).flat_params)      # the update really happened
     # (later steps can legitimately diverge: a 1e-6 difference in a parameter is enough to flip a near-tied candidate)
     tr.step(batches[0]); tr.step(batches[1])
