@@ -39,7 +39,7 @@ typedef struct leaf_engine* leaf_handle_t;
 enum { LEAF_ACT_GELU_ERF = 0, LEAF_ACT_QUICK_GELU = 1 };
 enum { LEAF_OBJ_L2 = 0, LEAF_OBJ_NEGL2 = 1, LEAF_OBJ_SIM = 2, LEAF_OBJ_DISSIM = 3 };
 enum { LEAF_CTX = 77, LEAF_SOT = 49406, LEAF_EOT = 49407, LEAF_VOCAB = 49408, LEAF_N_MERGES = 48894 };
-enum { LEAF_MAX_CAPTION_BYTES = 1000, LEAF_MAX_CAPTION_BYTES_LONG = 4072 };
+enum { LEAF_MAX_CAPTION_BYTES = 1000, LEAF_MAX_CAPTION_BYTES_LONG = 3560 };
 
 /* Text-tower shape: src/open_clip/model_configs/ViT-{L,H,g,bigG}-14.json "text_cfg" + "embed_dim". */
 typedef struct {
@@ -109,7 +109,9 @@ int leaf_reserve(leaf_handle_t h, int32_t max_seqs);
  *                  captions, whose hidden states the candidates share up to the edited word (see leaf_encode);
  *   base_out [R] : (may be NULL) for candidate rows the index of their sample's caption row (B*n + b), else -1
  * Token ids equal SimpleTokenizer's bit for bit. status_out (device int32[1], may be NULL) gets
- * OR-ed flags: 1 = an html entity expanded outside U+0000..U+00FF, 2 = non-ASCII caption byte. */
+ * OR-ed flags: 1 = an html entity expanded outside U+0000..U+024F (or entity text ftfy would unescape differently), 2 = text
+ * outside the domain (code point > U+024F, a capital whose lower case leaves it, a sequence ftfy would rewrite; any non-ASCII byte in
+ * HF-tokenizer mode), 4 = caption too long / edit position out of range. Captions are UTF-8. */
 int leaf_expand_tokenize(leaf_handle_t h, const uint8_t* caps, const int32_t* cap_off, int32_t B, int32_t n,
                          const int32_t* pos, const int32_t* chr, const int32_t* sel, const uint8_t* valid,
                          int32_t* tok_out, int32_t* len_out, int32_t* base_out, int32_t* status_out, void* stream);
@@ -119,7 +121,7 @@ int leaf_expand_tokenize(leaf_handle_t h, const uint8_t* caps, const int32_t* ca
  * eval_textfare.py:127): same BPE, no html.unescape, special tokens spelled <|startoftext|> / <|endoftext|>. */
 int leaf_set_tokenizer_mode(leaf_handle_t h, int32_t mode);
 /* Largest caption (UTF-8 bytes) the next leaf_expand_tokenize calls will see. Up to LEAF_MAX_CAPTION_BYTES (the default) the
- * kernel runs four candidates per CTA; beyond, up to LEAF_MAX_CAPTION_BYTES_LONG, its long-text variant (one per CTA) is used.
+ * kernel runs three candidates per CTA; beyond, up to LEAF_MAX_CAPTION_BYTES_LONG, its long-text variant (one per CTA) is used.
  * The reference's tokenizer takes text of any length (tokenizer.py:226-265); longer captions are flagged (status bit 4). */
 int leaf_set_max_caption_bytes(leaf_handle_t h, int32_t bytes);
 

@@ -357,9 +357,9 @@ extern "C" int leaf_load_bpe(leaf_handle_t e, const uint32_t* merge_pairs_host, 
   K1Tables T{};
   int rc;
   if ((rc = upload(e, k1host::k1_host_byte_id, 256, &T.byte_id))) return rc;
-  if ((rc = upload(e, k1host::k1_host_class, 256, &T.cls))) return rc;
-  if ((rc = upload(e, k1host::k1_host_ws, 256, &T.ws))) return rc;
-  if ((rc = upload(e, k1host::k1_host_lower, 256, &T.lower))) return rc;
+  if ((rc = upload(e, k1host::k1_host_class, K1_TABLE_CPS, &T.cls))) return rc;
+  if ((rc = upload(e, k1host::k1_host_ws, K1_TABLE_CPS, &T.ws))) return rc;
+  if ((rc = upload(e, k1host::k1_host_lower, K1_TABLE_CPS, &T.lower))) return rc;
   if ((rc = upload(e, k1host::k1_host_numref, 256, &T.numref))) return rc;
   if ((rc = upload(e, k1host::k1_host_ent_off, K1_N_ENTITIES, &T.ent_off))) return rc;
   if ((rc = upload(e, k1host::k1_host_ent_len, K1_N_ENTITIES, &T.ent_len))) return rc;

@@ -9,13 +9,14 @@
 //   whitespace_clean   tokenizer.py:72-75      lower: tokenizer.py:83-85
 //   regex split        tokenizer.py:160-163    bpe: tokenizer.py:172-211     row layout: tokenizer.py:256-263
 // html.unescape is CPython's Lib/html/__init__.py (_charref regex + _replace_charref) restated on code points
-// <= U+00FF. Domain: UTF-8 captions whose code points are all <= U+00FF (ASCII + Latin-1 Supplement: accented Western
-// European text), one LEAF edit, and whatever the two unescape passes make of that while staying <= U+00FF. Text is held
-// one byte per code point internally. Everything outside raises a status flag (the host raises LeafError), never a
-// silently different row: code points > U+00FF / malformed UTF-8; and the inputs on which ftfy.fix_text - which the
+// <= U+024F. Domain: UTF-8 captions whose code points are all <= U+024F (ASCII, Latin-1 Supplement, Latin Extended-A / -B:
+// Western and Central European text), one LEAF edit, and whatever the two unescape passes make of that while staying
+// <= U+024F. Text is held as 16-bit code points internally. Everything outside raises a status flag (the host raises
+// LeafError), never a silently different row: code points > U+024F / malformed UTF-8 / the 24 capitals whose str.lower()
+// leaves the range (U+0130 and the like); and the inputs on which ftfy.fix_text - which the
 // reference runs first and which cannot be restated here - is NOT the identity: C1 controls U+0080..U+009F (ftfy maps
-// them to Windows-1252), a UTF-8-lead-like character followed by a continuation-like one (`Ã©`: ftfy re-decodes
-// mojibake), a third level of entity nesting and ALL-CAPS entity names (`&EACUTE;`) in text without '<' (ftfy unescapes
+// them to Windows-1252), a UTF-8-lead-like character followed by a continuation-like one (`Ã©`, and the Windows-1252
+// spellings of continuation bytes such as `Å¡` / `Ãœ`: ftfy re-decodes mojibake), a third level of entity nesting and ALL-CAPS entity names (`&EACUTE;`) in text without '<' (ftfy unescapes
 // one level itself, with upper-case variants html.unescape does not know).
 #pragma once
 #include <stdint.h>
@@ -33,15 +34,17 @@ constexpr int K1_MAX_PIECES = 76;          // only the first 75 ids of a row can
 constexpr int K1_CTX = 77;
 constexpr int K1_SOT = 49406, K1_EOT = 49407;
 constexpr uint16_t K1_UNSUP_V = 0xFFFF, K1_EMPTY_V = 0xFFFE;
+constexpr int K1_MAX_CP = 0x24F;            // largest code point of the domain; tables have K1_MAX_CP + 1 entries
+typedef uint16_t k1_char;                   // one code point of the text being tokenized
 constexpr uint16_t K1_NO_RANK = 0xFFFF, K1_DIRTY = 0xFFFE;
 constexpr int K1_FLAG_ENTITY_DOMAIN = 1, K1_FLAG_NON_ASCII = 2 /* outside U+0000..U+00FF, or ftfy would rewrite it */, K1_FLAG_TOO_LONG = 4;
 constexpr uint64_t K1_SLOT_EMPTY = ~0ull;
 
 struct K1Tables {
   const uint16_t* byte_id;    // [256] id of each byte symbol (bytes_to_unicode order, tokenizer.py:31-51)
-  const uint8_t* cls;         // [256] regex class of the code point: 0 other, 1 \p{L}, 2 \p{N}, 3 \s
-  const uint8_t* ws;          // [256] str.split()/strip() whitespace
-  const uint8_t* lower;       // [256] str.lower()
+  const uint8_t* cls;         // [592] regex class of the code point: 0 other, 1 \p{L}, 2 \p{N}, 3 \s
+  const uint8_t* ws;          // [592] str.split()/strip() whitespace
+  const uint16_t* lower;      // [592] str.lower(), K1_UNSUP_V where it leaves the domain
   const uint16_t* numref;     // [256] outcome of &#N; for N < 256
   const uint16_t* ent_off;    // [n_ent] offsets into ent_blob (names sorted bytewise)
   const uint8_t* ent_len;     // [n_ent]
@@ -54,8 +57,8 @@ struct K1Tables {
 
 // per-candidate scratch (shared memory on the device)
 struct K1Scratch {
-  uint8_t* buf_a;             // [K1_MAX_TEXT]
-  uint8_t* buf_b;             // [K1_MAX_TEXT]
+  k1_char* buf_a;             // [K1_MAX_TEXT]
+  k1_char* buf_b;             // [K1_MAX_TEXT]
   uint16_t* sym;              // [2 * K1_MAX_TEXT] symbols of piece p live at sym + 2 * start(p)
   uint16_t* rk;               // [2 * K1_MAX_TEXT] rank cache, same indexing
   uint16_t* piece_start;      // [K1_MAX_PIECES]
@@ -82,16 +85,17 @@ K1_HD uint32_t k1_merge_rank(const K1Tables& T, uint32_t left, uint32_t right) {
   }
 }
 
-// ---- UTF-8 -> one byte per code point (U+0000..U+00FF); out may alias in (never longer than the input) -----
-K1_HD int k1_decode_utf8(const uint8_t* in, int n, uint8_t* out, int* flags) {
+// ---- UTF-8 -> 16-bit code points (U+0000..U+024F) ---------------------------------------------------------
+K1_HD int k1_decode_utf8(const uint8_t* in, int n, k1_char* out, int* flags) {
   int m = 0;
   for (int i = 0; i < n;) {
     const uint8_t b = in[i];
     if (b < 0x80) { out[m++] = b; ++i; }
-    else if ((b == 0xC2 || b == 0xC3) && i + 1 < n && (in[i + 1] & 0xC0) == 0x80) {
-      out[m++] = static_cast<uint8_t>(((b & 3) << 6) | (in[i + 1] & 0x3F));
+    else if (b >= 0xC2 && b <= 0xC9 && i + 1 < n && (in[i + 1] & 0xC0) == 0x80 &&
+             (((b & 0x1F) << 6) | (in[i + 1] & 0x3F)) <= K1_MAX_CP) {
+      out[m++] = static_cast<k1_char>(((b & 0x1F) << 6) | (in[i + 1] & 0x3F));
       i += 2;
-    } else {                                                // > U+00FF or malformed: flagged, one '?' per sequence
+    } else {                                                // > U+024F or malformed: flagged, one '?' per sequence
       *flags |= K1_FLAG_NON_ASCII;
       out[m++] = '?';
       ++i;
@@ -103,25 +107,26 @@ K1_HD int k1_decode_utf8(const uint8_t* in, int n, uint8_t* out, int* flags) {
 
 // ---- edit rule (utils_attacks.py:169-213) ---------------------------------------------
 // z even = slot before character z/2, z odd = character z/2. c = code point or -1.
-K1_HD int k1_apply_edit(const uint8_t* S, int len, int z, int c, uint8_t* out) {
+template <typename Ch>
+K1_HD int k1_apply_edit(const Ch* S, int len, int z, int c, Ch* out) {
   const int i = z >> 1;
   int n = 0;
   if (z & 1) {
     const bool del = (c == -1) || (c == static_cast<int>(S[i]));
     for (int j = 0; j < i; ++j) out[n++] = S[j];
-    if (!del) out[n++] = static_cast<uint8_t>(c);
+    if (!del) out[n++] = static_cast<Ch>(c);
     for (int j = i + 1; j < len; ++j) out[n++] = S[j];
   } else {
     const bool noop = (c == -1) || (c == '_');
     for (int j = 0; j < i; ++j) out[n++] = S[j];
-    if (!noop) out[n++] = static_cast<uint8_t>(c);
+    if (!noop) out[n++] = static_cast<Ch>(c);
     for (int j = i; j < len; ++j) out[n++] = S[j];
   }
   return n;
 }
 
 // ---- html.unescape, one pass -----------------------------------------------------------------------------
-K1_HD int k1_find_entity(const K1Tables& T, const uint8_t* s, int n) {
+K1_HD int k1_find_entity(const K1Tables& T, const k1_char* s, int n) {
   int lo = 0, hi = T.n_ent - 1;
   while (lo <= hi) {
     const int mid = (lo + hi) >> 1;
@@ -130,7 +135,7 @@ K1_HD int k1_find_entity(const K1Tables& T, const uint8_t* s, int n) {
     int cmp = 0;
     const int m = n < el ? n : el;
     for (int k = 0; k < m; ++k) {
-      if (s[k] != e[k]) { cmp = s[k] < e[k] ? -1 : 1; break; }
+      if (s[k] != e[k]) { cmp = s[k] < e[k] ? -1 : 1; break; }      // names are ASCII: a wider code point sorts after them
     }
     if (cmp == 0) cmp = (n < el) ? -1 : (n > el ? 1 : 0);
     if (cmp == 0) return mid;
@@ -139,25 +144,25 @@ K1_HD int k1_find_entity(const K1Tables& T, const uint8_t* s, int n) {
   return -1;
 }
 
-K1_HD bool k1_is_digit(uint8_t c) { return c >= '0' && c <= '9'; }
-K1_HD int k1_hexval(uint8_t c) {
+K1_HD bool k1_is_digit(k1_char c) { return c >= '0' && c <= '9'; }
+K1_HD int k1_hexval(k1_char c) {
   if (c >= '0' && c <= '9') return c - '0';
   if (c >= 'a' && c <= 'f') return c - 'a' + 10;
   if (c >= 'A' && c <= 'F') return c - 'A' + 10;
   return -1;
 }
 
-K1_HD int k1_emit_cp(uint16_t v, uint8_t* out, int m, int* flags) {
+K1_HD int k1_emit_cp(uint16_t v, k1_char* out, int m, int* flags) {
   if (v == K1_EMPTY_V) return m;
   if (v == K1_UNSUP_V) { *flags |= K1_FLAG_ENTITY_DOMAIN; out[m++] = '?'; return m; }
-  out[m++] = static_cast<uint8_t>(v);
+  out[m++] = v;
   return m;
 }
 
-K1_HD int k1_unescape(const K1Tables& T, const uint8_t* in, int n, uint8_t* out, int* flags, bool ftfy_caps = false) {
+K1_HD int k1_unescape(const K1Tables& T, const k1_char* in, int n, k1_char* out, int* flags, bool ftfy_caps = false) {
   int m = 0, i = 0;
   while (i < n) {
-    const uint8_t ch = in[i];
+    const k1_char ch = in[i];
     if (ch != '&' || i + 1 >= n) { out[m++] = ch; ++i; continue; }
     if (in[i + 1] == '#') {
       int j = i + 2;
@@ -185,7 +190,8 @@ K1_HD int k1_unescape(const K1Tables& T, const uint8_t* in, int n, uint8_t* out,
       if (num < 256u) v = T.numref[num];
       else if (num > 0x10FFFFu) v = K1_UNSUP_V;                                  // U+FFFD
       else if ((num >= 0xFDD0u && num <= 0xFDEFu) || (num & 0xFFFEu) == 0xFFFEu) v = K1_EMPTY_V;
-      else v = K1_UNSUP_V;                                                       // chr(num) > U+00FF (or U+FFFD)
+      else if (num <= static_cast<uint32_t>(K1_MAX_CP)) v = static_cast<uint16_t>(num);   // chr(num), inside the domain
+      else v = K1_UNSUP_V;                                                       // chr(num) > U+024F (or U+FFFD)
       m = k1_emit_cp(v, out, m, flags);
       i = j;
       continue;
@@ -193,13 +199,13 @@ K1_HD int k1_unescape(const K1Tables& T, const uint8_t* in, int n, uint8_t* out,
     // named: [^\t\n\f <&#;]{1,32};?
     int j = i + 1, cnt = 0;
     while (j < n && cnt < 32) {
-      const uint8_t c = in[j];
+      const k1_char c = in[j];
       if (c == '\t' || c == '\n' || c == '\f' || c == ' ' || c == '<' || c == '&' || c == '#' || c == ';') break;
       ++j; ++cnt;
     }
     if (cnt == 0) { out[m++] = ch; ++i; continue; }
     if (j < n && in[j] == ';') ++j;
-    const uint8_t* s = in + i + 1;
+    const k1_char* s = in + i + 1;
     const int sl = j - (i + 1);
     int e = k1_find_entity(T, s, sl);
     if (e >= 0) {
@@ -208,7 +214,7 @@ K1_HD int k1_unescape(const K1Tables& T, const uint8_t* in, int n, uint8_t* out,
       if (ftfy_caps && sl >= 3 && s[sl - 1] == ';') {         // &EACUTE; - ftfy knows upper-case variants, html.unescape does not
         bool caps = true, letter = false;
         for (int k = 0; k + 1 < sl; ++k) {
-          const uint8_t c = s[k];
+          const k1_char c = s[k];
           if (c >= 'A' && c <= 'Z') letter = true;
           else if (!(c >= '0' && c <= '9')) { caps = false; break; }
         }
@@ -233,32 +239,38 @@ K1_HD int k1_unescape(const K1Tables& T, const uint8_t* in, int n, uint8_t* out,
 }
 
 // ---- strip + " ".join(split()) + lower -------------------------------------------------------------------
-K1_HD int k1_clean(const K1Tables& T, const uint8_t* in, int n, uint8_t* out) {
+K1_HD int k1_clean(const K1Tables& T, const k1_char* in, int n, k1_char* out, int* flags) {
   int m = 0;
   bool pending_space = false;
   for (int i = 0; i < n; ++i) {
-    const uint8_t c = in[i];
+    const k1_char c = in[i];
     if (T.ws[c]) { pending_space = (m > 0); continue; }
     if (pending_space) { out[m++] = ' '; pending_space = false; }
-    out[m++] = T.lower[c];
+    k1_char lo = T.lower[c];
+    if (lo == K1_UNSUP_V) { *flags |= K1_FLAG_NON_ASCII; lo = '?'; }      // str.lower() leaves the domain (U+0130 -> i + U+0307, ...)
+    out[m++] = lo;
   }
   return m;
 }
 
-K1_HD bool k1_match(const uint8_t* t, int n, int pos, const char* lit, int ll) {
+// The reference's pattern is compiled with IGNORECASE and applied to lower-cased text: inside the domain the one character that
+// still matches an ASCII letter of the pattern's literals is U+017F (long s, folds to 's'): `'\u017f` is the contraction 's and
+// `<\u017ftart_of_text>` the special token (tools/make_tables.py asserts there is no other).
+K1_HD k1_char k1_fold(k1_char c) { return c == 0x17F ? static_cast<k1_char>('s') : c; }
+K1_HD bool k1_match(const k1_char* t, int n, int pos, const char* lit, int ll) {
   if (pos + ll > n) return false;
   for (int k = 0; k < ll; ++k)
-    if (t[pos + k] != static_cast<uint8_t>(lit[k])) return false;
+    if (k1_fold(t[pos + k]) != static_cast<k1_char>(lit[k])) return false;
   return true;
 }
 
 // ---- regex split of the cleaned text (tokenizer.py:160-163), first K1_MAX_PIECES pieces ------------------
 // piece_len gets 0x8000 | 0 for <start_of_text>, 0x8000 | 1 for <end_of_text> (ids straight from the cache,
 // tokenizer.py:159).
-K1_HD int k1_split(const K1Tables& T, const uint8_t* t, int n, uint16_t* piece_start, uint16_t* piece_len, bool hf = false) {
+K1_HD int k1_split(const K1Tables& T, const k1_char* t, int n, uint16_t* piece_start, uint16_t* piece_len, bool hf = false) {
   int np = 0, pos = 0;
   while (pos < n && np < K1_MAX_PIECES) {
-    const uint8_t c = t[pos];
+    const k1_char c = t[pos];
     const int cl = T.cls[c];
     if (cl == 3) { ++pos; continue; }
     int len = 0;
@@ -266,11 +278,15 @@ K1_HD int k1_split(const K1Tables& T, const uint8_t* t, int n, uint16_t* piece_s
     // transformers' CLIPTokenizer spells the two special tokens <|startoftext|> / <|endoftext|> (same lengths)
     if (c == '<' && k1_match(t, n, pos, hf ? "<|startoftext|>" : "<start_of_text>", 15)) { len = 15; special = 0x8000; }
     else if (c == '<' && k1_match(t, n, pos, hf ? "<|endoftext|>" : "<end_of_text>", 13)) { len = 13; special = 0x8001; }
+    if (special) {                     // the PIECE is cut case-insensitively, the id shortcut (tokenizer.py:159: the cache seeded
+      for (int k = 0; k < len; ++k)    // with the two literals) needs the exact spelling: `<\u017ftart_of_text>` is one ordinary piece
+        if (t[pos + k] == 0x17F) special = 0;
+    }
     else if (c == '\'' && pos + 1 < n) {
-      const uint8_t d = t[pos + 1];
+      const k1_char d = k1_fold(t[pos + 1]);
       if (d == 's' || d == 't' || d == 'm' || d == 'd') len = 2;
       else if (pos + 2 < n) {
-        const uint8_t e = t[pos + 2];
+        const k1_char e = t[pos + 2];
         if ((d == 'r' && e == 'e') || (d == 'v' && e == 'e') || (d == 'l' && e == 'l')) len = 3;
       }
     }
@@ -287,6 +303,13 @@ K1_HD int k1_split(const K1Tables& T, const uint8_t* t, int n, uint16_t* piece_s
   return np;
 }
 
+// what a UTF-8 continuation byte looks like after a wrong Latin-1 / Windows-1252 decode (inside the domain): U+0080..U+00BF, and
+// the Windows-1252 characters of the bytes 0x8C 0x9C 0x8A 0x9A 0x9F 0x8E 0x9E 0x83
+K1_HD bool k1_continuation_like(k1_char c) {
+  return (c >= 0x80 && c <= 0xBF) || c == 0x152 || c == 0x153 || c == 0x160 || c == 0x161 || c == 0x178 || c == 0x17D || c == 0x17E ||
+         c == 0x192;
+}
+
 // ---- everything a candidate needs before BPE (serial; lane 0 on the device) ------------------------------
 // src = caption bytes; do_edit selects the LEAF edit (z, c); returns flags.
 // hf = true: the tokenizer of HF's CLIPTokenizer as the reference's eval path uses it (utils_attacks.py:67-71) - no
@@ -300,19 +323,19 @@ K1_HD int k1_prepare(const K1Tables& T, const uint8_t* src, int len, bool do_edi
   else for (int i = 0; i < n; ++i) S.buf_a[i] = S.buf_b[i];
   bool amp = false, lt = false;
   for (int i = 0; i < n; ++i) {
-    const uint8_t ch = S.buf_a[i];
-    if (ch & 0x80) {
+    const k1_char ch = S.buf_a[i];
+    if (ch >= 0x80) {
       if (hf) flags |= K1_FLAG_NON_ASCII;                   // HF mode stays ASCII: BasicTokenizer drops U+00AD and other controls
       else if (ch <= 0x9F) flags |= K1_FLAG_NON_ASCII;      // C1 control: ftfy rewrites it as Windows-1252
-      else if (ch >= 0xC2 && ch <= 0xF4 && i + 1 < n && S.buf_a[i + 1] >= 0x80 && S.buf_a[i + 1] <= 0xBF)
-        flags |= K1_FLAG_NON_ASCII;                         // looks like UTF-8 read as Latin-1: ftfy re-decodes it
+      else if (ch >= 0xC2 && ch <= 0xF4 && i + 1 < n && k1_continuation_like(S.buf_a[i + 1]))
+        flags |= K1_FLAG_NON_ASCII;                         // looks like UTF-8 read as Latin-1 / Windows-1252: ftfy re-decodes it
     }
     if (hf && (ch == 0x7f || (ch < 0x20 && ch != 9 && ch != 10 && ch != 13))) flags |= K1_FLAG_NON_ASCII;
     amp |= (ch == '&');
     lt |= (ch == '<');
   }
   if (hf) amp = false;
-  const uint8_t* cur = S.buf_a;
+  const k1_char* cur = S.buf_a;
   if (amp) {                                               // html.unescape(html.unescape(text))
     n = k1_unescape(T, S.buf_a, n, S.buf_b, &flags, !lt);
     n = k1_unescape(T, S.buf_b, n, S.buf_a, &flags);
@@ -324,7 +347,7 @@ K1_HD int k1_prepare(const K1Tables& T, const uint8_t* src, int len, bool do_edi
       if (!same) flags |= K1_FLAG_ENTITY_DOMAIN;
     }
   }
-  n = k1_clean(T, cur, n, S.buf_b);
+  n = k1_clean(T, cur, n, S.buf_b, &flags);
   S.text_len = n;
   S.n_pieces = k1_split(T, S.buf_b, n, S.piece_start, S.piece_len, hf);
   return flags;
@@ -342,10 +365,10 @@ K1_HD void k1_encode_piece(const K1Tables& T, K1Scratch& S, int p) {
     S.piece_len[p] = 1;
     return;
   }
-  const uint8_t* t = S.buf_b + start;
+  const k1_char* t = S.buf_b + start;
   int n = 0;
-  for (int i = 0; i < pl; ++i) {                           // UTF-8 bytes of the code points -> byte symbols
-    const uint8_t cp = t[i];
+  for (int i = 0; i < pl; ++i) {                           // UTF-8 bytes of the code points (all < U+0800: 1 or 2 bytes) -> byte symbols
+    const k1_char cp = t[i];
     if (cp < 0x80) sym[n++] = T.byte_id[cp];
     else { sym[n++] = T.byte_id[0xC0 | (cp >> 6)]; sym[n++] = T.byte_id[0x80 | (cp & 0x3F)]; }
   }

@@ -1,5 +1,5 @@
 // K1 kernel: candidate expansion + CLIP BPE tokenization, one warp per candidate (sm_100a). Captions are UTF-8 with code
-// points <= U+00FF (k1_core.cuh: domain); edit positions count code points, as Python's str does.
+// points <= U+024F (k1_core.cuh: domain); edit positions count code points, as Python's str does.
 //   lanes 0..31 copy the caption into shared memory with 16-byte loads when the source is aligned,
 //   lane 0 applies the edit, unescapes, cleans and splits (serial, a few hundred byte operations),
 //   lanes take regex pieces round-robin and run the BPE merge loop on them (merge ranks from an L2-resident
@@ -14,8 +14,8 @@
 
 namespace leaf {
 
-constexpr int K1_WARPS_PER_CTA = 4;          // default variant: captions up to 1000 bytes, 4 warps x 11 KB of scratch per CTA
-constexpr int K1_LONG_TEXT = 4096;           // long variant: captions up to 4072 bytes, one warp (45 KB of scratch) per CTA
+constexpr int K1_WARPS_PER_CTA = 3;          // default variant: captions up to 1000 bytes, 3 warps x 13 KB of scratch per CTA
+constexpr int K1_LONG_TEXT = 3584;           // long variant: captions up to 3560 bytes, one warp (46 KB of scratch) per CTA
 
 struct K1Args {
   const uint8_t* caps;
@@ -35,8 +35,8 @@ struct K1Args {
 template <int MAXT, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) k1_expand_tokenize_kernel(const K1Tables T, const K1Args a) {
   __shared__ __align__(16) uint8_t s_src[WARPS][MAXT];
-  __shared__ __align__(16) uint8_t s_a[WARPS][MAXT];
-  __shared__ __align__(16) uint8_t s_b[WARPS][MAXT];
+  __shared__ __align__(16) k1_char s_a[WARPS][MAXT];
+  __shared__ __align__(16) k1_char s_b[WARPS][MAXT];
   __shared__ uint16_t s_sym[WARPS][2 * MAXT];
   __shared__ uint16_t s_rk[WARPS][2 * MAXT];
   __shared__ uint16_t s_ps[WARPS][K1_MAX_PIECES];

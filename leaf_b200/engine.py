@@ -26,7 +26,8 @@ CONTEXT_LENGTH = 77
 OBJECTIVES = {"l2": 0, "negl2": 1, "sim": 2, "dissim": 3}
 STATUS_ENTITY_DOMAIN, STATUS_NON_ASCII, STATUS_TOO_LONG = 1, 2, 4
 MAX_CAPTION_BYTES = 1000            # the tokenizer kernel's default variant; up to MAX_CAPTION_BYTES_LONG with its long-text variant
-MAX_CAPTION_BYTES_LONG = 4072
+MAX_CAPTION_BYTES_LONG = 3560
+MAX_CODE_POINT = 0x24F               # csrc/k1_core.cuh: ASCII, Latin-1 Supplement, Latin Extended-A / -B
 
 
 def _ptr(t):
@@ -172,13 +173,13 @@ class LeafEngine:
     @staticmethod
     def pack_captions(sentences):
         """list[str] -> (uint8 caption bytes back to back, int32 [B+1] BYTE offsets). Captions travel as UTF-8; the kernel's
-        domain is code points <= U+00FF (ASCII + Latin-1 Supplement; csrc/k1_core.cuh), checked here for a clear message and
+        domain is code points <= U+024F (ASCII, Latin-1 Supplement, Latin Extended-A / -B; csrc/k1_core.cuh), checked here for a clear message and
         again on the device. The buffer tail is padded so the kernel's 16-byte loads never leave the allocation."""
         blobs = []
         for s in sentences:
-            if not s.isascii() and max(map(ord, s)) > 0xFF:
-                bad = next(c for c in s if ord(c) > 0xFF)
-                raise LeafError(f"caption outside the tokenizer kernel's domain (code points <= U+00FF): U+{ord(bad):04X} in {s!r}")
+            if not s.isascii() and max(map(ord, s)) > MAX_CODE_POINT:
+                bad = next(c for c in s if ord(c) > MAX_CODE_POINT)
+                raise LeafError(f"caption outside the tokenizer kernel's domain (code points <= U+{MAX_CODE_POINT:04X}): U+{ord(bad):04X} in {s!r}")
             b = s.encode("utf-8")
             if len(b) > MAX_CAPTION_BYTES_LONG:
                 raise LeafError(f"caption longer than {MAX_CAPTION_BYTES_LONG} bytes")
@@ -244,10 +245,11 @@ class LeafEngine:
         st = int(self._status.item())
         if st:
             self._status.zero_()
-            what = [m for bit, m in ((1, "an html entity expanded outside U+0000..U+00FF, or entity text ftfy would unescape differently "
+            what = [m for bit, m in ((1, "an html entity expanded outside U+0000..U+024F, or entity text ftfy would unescape differently "
                                          "(third nesting level / ALL-CAPS name)"),
-                                     (2, "text outside the kernel's domain: code point > U+00FF, a C1 control, a Latin-1 sequence ftfy "
-                                         "would re-decode as mojibake, or any non-ASCII byte in HF-tokenizer mode / the --constrain filter"),
+                                     (2, "text outside the kernel's domain: code point > U+024F, a capital whose lower case leaves that range, a C1 "
+                                         "control, a sequence ftfy would re-decode as mojibake, or any non-ASCII byte in HF-tokenizer mode / "
+                                         "the --constrain filter"),
                                      (4, "caption too long / position out of range"),
                                      (8, "sentence longer than the constraint filter accepts (511 bytes)"),
                                      (16, "constraint filter buffer overflow")) if st & bit]

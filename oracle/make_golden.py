@@ -113,11 +113,16 @@ LATIN1_CAPTIONS = [
     "a\u00a0b non\u00a0breaking  spaces\u00a0", "Crème brûlée's déjà-vu: voilà!it's", "ß", "É", "éé 12½x ·middle· ¬not ¦bar ¨uml ¯macr ´acute ¸cedil",
     "soft\u00adhyphen in\u00adside", "£5 ¥6 ¢7 ¤8 and 9€-less", "Ò Ó Ô Õ Ö Ø Ù Ú Û Ü Ý à á â ã ä å æ ç è é ê ë ì í î ï ð ñ ò ó ô õ ö ø ù ú û ü ý þ ÿ",
     "À Á Â Ã Ä Å Æ Ç È É Ê Ë Ì Í Î Ï Ð Ñ", "façade&amp;café &eacute;t&eacute; &Eacute;T&Eacute; &#233; &#xE9;", "l'été d'août m'a plu 's 't 're",
+    # Latin Extended-A / -B (U+0100..U+024F): Central European, Baltic, Romanian, Turkish (without U+0130), Vietnamese base letters
+    "Zażółć gęślą jaźń w Łodzi", "Příliš žluťoučký kůň úpěl ďábelské ódy", "Árvíztűrő tükörfúrógép ŐŰ", "ȘTEFAN și ȚARA: mâță în București",
+    "Ğğ Şş ı dotless and ǅ ǆ Ǆ digraphs Ǉǈǉ", "Ēēģīķļņū Šš Žž Ąą Ęę Ėė Įį Ųų", "\u017fhort long-s it'\u017f <\u017ftart_of_text> x", "Œuvre cœur Ÿ ÿ ƒ Ǝ ǝ Ȝ ȝ",
+    "&Scaron;koda &zcaron;ena &#256;&#257; &#x17D; &OElig;&oelig; &Yuml; &fnof;", "ĀĂĄĆĈĊČĎĐĒĔĖĘĚĜĞĠĢĤĦĨĪĬĮĲĴĶĹĻĽĿŁŃŅŇŊŌŎŐŒŔŖŘŚŜŞŠŢŤŦŨŪŬŮŰŲŴŶŸŹŻŽ",
 ]
 
 
 def gen_tokenizer_latin1():
-    """Captions with code points in U+0080..U+00FF (the Latin-1 Supplement K1 accepts as UTF-8 input): the reference's
+    """Captions with code points in U+0080..U+024F (Latin-1 Supplement, Latin Extended-A / -B: what K1 accepts as UTF-8 input
+    beyond ASCII): the reference's
     SimpleTokenizer on the captions and on attack-shaped edits of them (utils_attacks.generate_sentence, positions counted in
     code points). ftfy is the identity shim here, as for every other fixture; K1 flags the Latin-1 inputs on which the real
     ftfy would not be (C1 controls, mojibake-shaped pairs) and none of these captions is one of them, except the pairs an
@@ -125,7 +130,7 @@ def gen_tokenizer_latin1():
     fixture (their token ids are still what SimpleTokenizer produces under the shim) and marked."""
     tok = open_clip.get_tokenizer("ViT-L-14")
     rng = random.Random(23)
-    caps = [c for c in LATIN1_CAPTIONS if c.isascii() or max(map(ord, c)) <= 0xFF]
+    caps = [c for c in LATIN1_CAPTIONS if c.isascii() or max(map(ord, c)) <= 0x24F]
     assert len(caps) == len(LATIN1_CAPTIONS) - 1                                   # the one with the euro sign is dropped
     enc = [[t, tok.encode(t)] for t in caps]
     edits = []

@@ -26,8 +26,8 @@ extern "C" int k1h_expand_tokenize(const uint8_t* caps, const int32_t* cap_off, 
                                    const int32_t* chr, const int32_t* sel, const uint8_t* valid, int32_t* tok_out,
                                    int32_t* len_out) {
   K1Tables T = k1_host_tables(g_tab.data());
-  constexpr int MAXT = 4096;                 // the long-text variant's buffers (k1_tokenize.cuh: K1_LONG_TEXT)
-  std::vector<uint8_t> a(MAXT), b(MAXT);
+  constexpr int MAXT = 3584;                 // the long-text variant's buffers (k1_tokenize.cuh: K1_LONG_TEXT)
+  std::vector<k1_char> a(MAXT), b(MAXT);
   std::vector<uint16_t> sym(2 * MAXT), rk(2 * MAXT), ps(K1_MAX_PIECES), pl(K1_MAX_PIECES);
   K1Scratch S{a.data(), b.data(), sym.data(), rk.data(), ps.data(), pl.data(), 0, 0};
   int flags = 0;

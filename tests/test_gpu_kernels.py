@@ -256,7 +256,7 @@ def test_k1_golden_strings(eng, golden_dir):
 
 
 def test_k1_latin1_utf8_captions(eng, golden_dir):
-    """Accented captions (UTF-8, code points <= U+00FF) on the device: the reference's SimpleTokenizer rows, attack-shaped
+    """Accented captions (UTF-8, code points <= U+024F) on the device: the reference's SimpleTokenizer rows, attack-shaped
     edits with positions counted in code points, the whole attack on such captions, and LeafError beyond the domain."""
     from leaf_b200 import LeafError, attack_text_leaf
     g = json.load(open(os.path.join(golden_dir, "tokenizer_latin1_golden.json")))
@@ -279,23 +279,25 @@ def test_k1_latin1_utf8_captions(eng, golden_dir):
     feats, adv = attack_text_leaf(eng, None, caps, anchor, "cuda", n=12, k=2)
     assert all(abs(len(a) - len(c)) <= 2 for a, c in zip(adv, caps)) and adv != caps
     assert torch.equal(eng.encode_tokens(eng.tokenize(adv)), feats)
-    for bad in ("\u0141\u00f3d\u017a", "emoji \U0001F600"):
-        with pytest.raises(LeafError, match="U\\+00FF"):
+    for bad in ("na\u00efve \u0250", "emoji \U0001F600"):
+        with pytest.raises(LeafError, match="U\\+024F"):
             eng.tokenize([bad])
+    with pytest.raises(LeafError, match="domain"):
+        eng.tokenize(["\u0130stanbul"])                                           # str.lower() leaves the domain
     with pytest.raises(LeafError, match="domain"):
         eng.tokenize(["mojibake Ã©"])
     eng._status.zero_()
 
 
 def test_k1_long_captions(eng):
-    """Captions of 1000-4072 bytes switch the tokenizer kernel to its long-text variant (sticky per engine); rows equal the oracle's
+    """Captions of 1000-3560 bytes switch the tokenizer kernel to its long-text variant (sticky per engine); rows equal the oracle's
     and the CPU-compiled core's, the attack runs on them, and longer captions raise."""
     from leaf_b200 import LeafError, attack_text_leaf, synth
     from leaf_b200.tower import LeafTextTower
     from oracle import leaf_oracle as O
     from tests import k1_harness as H
     e = LeafTextTower.random("tiny", seed=2).leaf_engine                     # its own engine: the switch is sticky
-    caps = [" ".join(synth.make_captions(40, seed=s))[:L] for s, L in ((1, 1500), (2, 2600), (3, 4072))] + ["short one", "caf\u00e9 " * 500]
+    caps = [" ".join(synth.make_captions(40, seed=s))[:L] for s, L in ((1, 1500), (2, 2600), (3, 3560))] + ["short one", "caf\u00e9 " * 500]
     assert torch.equal(e.tokenize(caps).cpu(), O.OracleTokenizer()(caps))
     rng = np.random.RandomState(0)
     n = 16
@@ -309,7 +311,7 @@ def test_k1_long_captions(eng):
     feats, adv = attack_text_leaf(e, None, caps, anchor, "cuda", n=8, k=1)
     assert torch.equal(e.encode_tokens(e.tokenize(adv)), feats) and all(abs(len(a) - len(c)) <= 1 for a, c in zip(adv, caps))
     with pytest.raises(LeafError, match="longer"):
-        e.tokenize(["z" * 4073])
+        e.tokenize(["z" * 3561])
 
 
 def test_k1_candidates_bit_exact(eng):
@@ -340,9 +342,9 @@ def test_k1_candidates_bit_exact(eng):
 def test_k1_flags_out_of_domain(eng):
     from leaf_b200 import LeafError
     from oracle import leaf_oracle as O
-    assert torch.equal(eng.tokenize(["café"]).cpu(), O.OracleTokenizer()(["café"]))       # Latin-1 is inside the domain now
+    assert torch.equal(eng.tokenize(["café"]).cpu(), O.OracleTokenizer()(["café"]))       # Latin-1 / Latin Extended is inside the domain now
     with pytest.raises(LeafError):
-        eng.tokenize(["caf\u00e9 \u0142"])                                                 # U+0142 is not
+        eng.tokenize(["caf\u00e9 \u0250"])                                                 # U+0250 is not
     with pytest.raises(LeafError):
         eng.tokenize(["x &lambda; y"])
     with pytest.raises(LeafError):
