@@ -44,3 +44,30 @@ def test_open_clip_module_detection():
         _open_clip_config(torch.nn.Linear(2, 2))
     with pytest.raises(LeafError, match="naming"):
         _canon_state({"weight": torch.zeros(2)})
+
+
+def test_real_open_clip_models_are_recognised():
+    """The reference's own model classes (open_clip.create_model through oracle/ref_shims), where /root/reference exists (this
+    container; the GPU box does not have it): CLIP with nn.GELU and with QuickGELU, heads, eps, layout, and the DDP-style holder."""
+    import os
+    import subprocess
+    import sys
+    ref = os.environ.get("LEAF_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src", "open_clip")):
+        pytest.skip("reference tree not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = r'''
+import sys, torch
+sys.path[:0] = [ROOT + "/oracle/ref_shims", REF + "/src", REF, ROOT]
+import open_clip
+from leaf_b200.engine import _canon_state, _open_clip_config
+for name, quick, heads, layers, width in (("ViT-B-32", False, 8, 12, 512), ("ViT-B-32-quickgelu", True, 8, 12, 512), ("ViT-L-14", False, 12, 12, 768)):
+    m = open_clip.create_model(name, pretrained=None)
+    assert _open_clip_config(m) == (heads, quick, 1e-5), (name, _open_clip_config(m))
+    holder = torch.nn.Module(); holder.module = m
+    c = _canon_state({k: v for k, v in m.state_dict(keep_vars=True).items()})
+    assert c["layout"] == "open_clip" and len(c["layers"]) == layers and c["tok"].shape[1] == width and c["proj_is_ew"] == 0
+print("OK")
+'''.replace("ROOT", repr(root)).replace("REF", repr(ref))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-3000:]
