@@ -230,6 +230,33 @@ def gen_attack():
     print("attack cases", len(cases))
 
 
+def gen_attack_latin():
+    """attack_text_leaf of the reference on ACCENTED captions (code points up to U+024F, positions drawn over code points):
+    the whole attack on the K1 kernel's widened input domain, k = 1 and k = 2."""
+    tok = open_clip.get_tokenizer("ViT-L-14")
+    cfg = synth.TOWERS["tiny"]
+    sd = synth.random_tower_state_dict(cfg, seed=31, exact_numpy=True)
+    sd_frozen = synth.perturbed_copy(sd, seed=32, std=1e-2, exact_numpy=True)
+    model = build_ref_clip(cfg, sd)
+    frozen = build_ref_clip(cfg, sd_frozen)
+    pool = [c for c in LATIN1_CAPTIONS if not c.isascii() and max(map(ord, c)) <= 0x24F and "&" not in c and "\u017f" not in c and len(c) > 12]
+    cases, arrays = [], {}
+    for ci, (lo, hi, n, k, seed) in enumerate([(0, 6, 24, 1, 0), (6, 12, 40, 1, 1), (12, 17, 16, 2, 2)]):
+        caps = pool[lo:hi]
+        with torch.no_grad():
+            anchor = frozen.encode_text(tok(caps), normalize=False)
+            np.random.seed(seed)
+            feats, adv = utils_attacks.attack_text_leaf(model, tok, caps, anchor.clone(), "cpu", objective="l2", n=n, k=k, V=V,
+                                                        constrain=False)
+        cases.append(dict(B=len(caps), n=n, k=k, seed=seed, objective="l2", captions=caps, adv=adv))
+        arrays[f"anchor_{ci}"] = anchor.numpy()
+        arrays[f"feats_{ci}"] = feats.numpy()
+    json.dump({"tower": "tiny", "seed": 31, "frozen_seed": 32, "frozen_std": 1e-2, "cases": cases},
+              open(os.path.join(OUT, "attack_latin_golden.json"), "w"))
+    np.savez_compressed(os.path.join(OUT, "attack_latin_golden.npz"), **arrays)
+    print("accented attack cases", len(cases), [c["B"] for c in cases])
+
+
 def gen_eval_attacks():
     """attack_text_charmer_inference / attack_text_bruteforce (utils_attacks.py:395-580), one sentence at a time."""
     tok = open_clip.get_tokenizer("ViT-L-14")
@@ -334,6 +361,7 @@ if __name__ == "__main__":
         sys.exit(0)
     if sys.argv[1:] == ["latin1"]:
         gen_tokenizer_latin1()
+        gen_attack_latin()
         sys.exit(0)
     gen_convert_ids()
     gen_edit()
@@ -343,3 +371,4 @@ if __name__ == "__main__":
     gen_eval_attacks()
     gen_hf_tokenizer()
     gen_tokenizer_latin1()
+    gen_attack_latin()

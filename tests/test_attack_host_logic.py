@@ -36,6 +36,19 @@ def test_attack_driver_reproduces_reference_runs():
         assert np.abs(feats.numpy() - z[f"feats_{ci}"]).max() < 1e-4
 
 
+def test_attack_driver_on_accented_captions():
+    """The same on captions with code points up to U+024F: UTF-8 on the wire, positions in code points, the K1 core's wider domain."""
+    g = json.load(open(os.path.join(GOLDEN, "attack_latin_golden.json")))
+    z = np.load(os.path.join(GOLDEN, "attack_latin_golden.npz"))
+    cfg = synth.TOWERS[g["tower"]]
+    eng = OracleEngine(synth.random_tower_state_dict(cfg, seed=g["seed"], exact_numpy=True), cfg.heads)
+    for ci, c in enumerate(g["cases"]):
+        np.random.seed(c["seed"])
+        feats, adv = attack_text_leaf(eng, None, c["captions"], torch.from_numpy(z[f"anchor_{ci}"]).clone(), "cpu", n=c["n"], k=c["k"])
+        assert adv == c["adv"], ci
+        assert np.abs(feats.numpy() - z[f"feats_{ci}"]).max() < 1e-4
+
+
 def _levenshtein(a, b):
     prev = list(range(len(b) + 1))
     for i, ca in enumerate(a, 1):

@@ -205,6 +205,40 @@ def test_attack_golden_cases(golden_dir):
     assert agree / total >= 0.99, (agree, total)
 
 
+def test_attack_on_accented_captions_golden(golden_dir):
+    """attack_text_leaf on captions with code points up to U+024F against the reference's own runs (attack_latin_golden.*):
+    winners must agree wherever the oracle's decisions are clear of the loss tolerance."""
+    from leaf_b200 import attack_text_leaf, synth
+    from leaf_b200.tower import LeafTextTower
+    from oracle import leaf_oracle as O
+    g = json.load(open(os.path.join(golden_dir, "attack_latin_golden.json")))
+    z = np.load(os.path.join(golden_dir, "attack_latin_golden.npz"))
+    cfg = synth.TOWERS[g["tower"]]
+    sd = synth.random_tower_state_dict(cfg, seed=g["seed"], exact_numpy=True)
+    tower = LeafTextTower(sd, heads=cfg.heads)
+    otok = O.OracleTokenizer()
+    enc = lambda t, normalize: O.encode_text({k: v.float() for k, v in sd.items()}, t, cfg.heads, normalize=normalize)
+    total = agree = 0
+    for ci, c in enumerate(g["cases"]):
+        anchor = torch.from_numpy(z[f"anchor_{ci}"])
+        np.random.seed(c["seed"])
+        feats, adv = attack_text_leaf(tower, None, c["captions"], anchor.clone().cuda(), "cuda", n=c["n"], k=c["k"])
+        assert torch.equal(tower.encode_text(tower.tokenizer(adv)), feats)
+        np.random.seed(c["seed"])
+        trace = {}
+        _, oadv = O.attack_text_leaf_oracle(enc, otok, c["captions"], anchor, n=c["n"], k=c["k"], trace=trace)
+        assert oadv == c["adv"]
+        if c["k"] == 1:
+            r = trace["rounds"][0]
+            for b in range(c["B"]):
+                clear = all(bool((torch.topk(l[b], 2).values[0] - torch.topk(l[b], 2).values[1]).abs() > LOSS_RTOL * torch.topk(l[b], 2).values[0].abs())
+                            for l in (r["loss1"], r["loss2"]))
+                if clear:
+                    total += 1
+                    agree += int(adv[b] == c["adv"][b])
+    assert total >= 5 and agree == total, (agree, total)
+
+
 def test_attack_full_config_vs_oracle_scores():
     """BASELINE config 1 shape (ViT-L-14 tower, k=1, rho=50) on a reduced batch: every candidate's TextFARE loss
     against the fp32 oracle (rel. err <= 1e-2) and the selected candidates (>= 99 % on non-tied scores)."""
