@@ -29,7 +29,7 @@ the reference's lower-cased domain - tests/test_constrain_cpu.py). The functions
     abbreviation set is whatever the caller passes (engine.load_words(..., abbrev=...)), not english.pickle's.
 
 The CUDA kernel (leaf_b200/csrc/constrain_core.cuh) is pinned bit-exactly against THIS module; this module is what a
-user with NLTK installed should check first (tools/validate_constrain.py does that and reports the mismatch rate).
+user with NLTK installed should check first (tests/tools/validate_constrain.py does that and reports the mismatch rate).
 """
 from __future__ import annotations
 

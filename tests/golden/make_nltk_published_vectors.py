@@ -6,7 +6,7 @@ sent_tokenize followed by NLTKWordTokenizer.tokenize).
 NLTK is not installed in this image and cannot be fetched (no network), so these vectors could NOT be produced by running
 NLTK here. They are the doctest / unit-test examples of the NLTK 3.8.1 sources, transcribed by hand with the file and the
 docstring or test they come from; none of the expected outputs was produced by oracle/nltk_restate.py or by the CUDA
-kernel - that is the point of the file. `tools/validate_constrain.py --published` re-checks every vector against a real
+kernel - that is the point of the file. `tests/tools/validate_constrain.py --published` re-checks every vector against a real
 NLTK install when one is reachable and reports any transcription error.
 
 kind:

@@ -5,7 +5,8 @@ rounded to bf16; loss relative error of the second against the first."""
 import os, sys
 import numpy as np, torch
 import torch.nn.functional as F
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 from leaf_b200 import synth
 from oracle import leaf_oracle as O
 

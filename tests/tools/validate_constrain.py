@@ -3,7 +3,7 @@
 restatement of the reference's `--constrain` filter (oracle/nltk_restate.py, which the CUDA kernel is pinned to) differs
 from NLTK itself - the parity this repo could not pin offline. No GPU needed.
 
-    python tools/validate_constrain.py [captions.txt]        # one caption per line; default: built-in samples
+    python tests/tools/validate_constrain.py [captions.txt]        # one caption per line; default: built-in samples
 
 It also replays tests/golden/nltk_published_vectors.json (NLTK's own docstring / doctest / unit-test examples, transcribed by
 hand because NLTK is not installable in the build image) through the installed NLTK and reports every transcription error,
@@ -14,7 +14,8 @@ import os
 import random
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 from oracle import nltk_restate as N  # noqa: E402
 
 try:
@@ -39,7 +40,7 @@ V = [-1] + [ord(c) for c in "abcdefghijklmnopqrstuvwxyz ABCDEFGHIJKLMNOPQRSTUVWX
 from oracle.leaf_oracle import edit_sentence  # noqa: E402
 
 report = []
-pub = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "nltk_published_vectors.json")))
+pub = json.load(open(os.path.join(ROOT, "tests", "golden", "nltk_published_vectors.json")))
 from nltk.tokenize import NLTKWordTokenizer, sent_tokenize  # noqa: E402
 wrong = 0
 for v in pub["vectors"]:
@@ -61,6 +62,6 @@ for S in caps:
             report.append(f"DIFF {s!r}\n   nltk: {a}\n   restatement: {b}")
 report.append(f"{tot} candidates: token lists differ on {tok_bad} ({tok_bad / tot:.2%}), dictionary-word counts on {cnt_bad} ({cnt_bad / tot:.2%})")
 print("\n".join(report))
-out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "constrain_vs_nltk_report.txt")
+out = os.path.join(ROOT, "profiles", "constrain_vs_nltk_report.txt")
 open(out, "w").write("\n".join(report) + "\n")
 print("written to", out)
