@@ -114,6 +114,7 @@ struct leaf_engine {
   int* first_of = nullptr;            // [max_seqs] sequence whose rows stand for sequence i
   bool prune_last = true;             // final layer: out-proj + MLP on the pooled rows only
   int gemm_sm_budget = 0;             // > 0: the persistent GEMM grids use at most this many SMs (leaf_set_sm_budget)
+  int pdl = 1;                        // launch the per-layer chain with programmatic dependent launch (LEAF_PDL=0 turns it off)
   int att_impl = 1;                   // 1 = register-fed attention_kernel (default: faster in situ), 2 = cp.async ring attention2_kernel (LEAF_ATTENTION_IMPL=2)
   int *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr, *dup_of = nullptr, *need = nullptr;
   int4* meta = nullptr;
@@ -245,11 +246,13 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = GEMM2_SMEM_BYTES;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see pdl_wait() in gemm_sm100.cuh
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = e->pdl ? 2 : 1;
   switch (epi) {
     case EPI_BF16: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_BF16>, ta, tb, p)); break;
     case EPI_BF16_ACT: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_BF16_ACT>, ta, tb, p)); break;
@@ -297,6 +300,7 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
   CK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   if (const char* ai = getenv("LEAF_ATTENTION_IMPL")) e->att_impl = atoi(ai) == 2 ? 2 : 1;
+  if (const char* pd = getenv("LEAF_PDL")) e->pdl = atoi(pd) != 0;
   CK(cudaFuncSetAttribute(attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, attb_smem_bytes(LEAF_CTX)));
   *out = e;
   return LEAF_OK;
@@ -501,6 +505,22 @@ extern "C" int leaf_expand_tokenize(leaf_handle_t e, const uint8_t* caps, const 
   return LEAF_OK;
 }
 
+// A launch that may start while the previous kernel of the stream drains (programmatic dependent launch): the kernel
+// must call pdl_wait() before its first global access (gemm_sm100.cuh).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(const leaf_engine* e, void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = e->pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev, int rows_max, const int* gather,
                             const float* g, const float* b, __nv_bfloat16* y, cudaStream_t st,
                             const __nv_bfloat16* delta = nullptr, __nv_bfloat16* y_lo = nullptr) {
@@ -512,7 +532,7 @@ static int launch_layernorm(leaf_engine* e, const float* x, const int* rows_dev,
   const int cap = e->sm_count * 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-#define LN_CASE(V) case V: layernorm_bf16_kernel<V><<<blocks, 256, 0, st>>>(x, rows_dev, rows_max, gather, W, g, b, e->cfg.ln_eps, y, delta, y_lo); break;
+#define LN_CASE(V) case V: CK(launch_pdl(e, layernorm_bf16_kernel<V>, dim3(blocks), dim3(256), st, x, rows_dev, rows_max, gather, W, g, b, e->cfg.ln_eps, y, delta, y_lo)); break;
   switch (vpl) {
     LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8)
     LN_CASE(9) LN_CASE(10) LN_CASE(11) LN_CASE(12) LN_CASE(13) LN_CASE(14) LN_CASE(15) LN_CASE(16)
@@ -538,7 +558,7 @@ static int launch_attention(leaf_engine* e, const __nv_bfloat16* qkv, const int4
     return LEAF_OK;
   }
   const int grid = (N * H + ATT_WARPS - 1) / ATT_WARPS;
-  attention_kernel<<<grid, ATT_WARPS * 32, 0, st>>>(qkv, meta, N, H, W, out, last_only);
+  CK(launch_pdl(e, attention_kernel, dim3(grid), dim3(ATT_WARPS * 32), st, qkv, meta, N, H, W, out, last_only));
   e->launches++;
   CK(cudaGetLastError());
   return LEAF_OK;

@@ -127,6 +127,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   cluster_sync_all();                       // barriers of both CTAs initialised, TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_gen;
+  // Everything above overlapped the previous kernel's tail (engine.cu launches every GEMM with programmatic stream
+  // serialization); its output is read below. The GEMM itself never calls pdl_trigger(): a LayerNorm / attention grid that
+  // becomes resident next to still-draining GEMM CTAs keeps those SMs in the GEMM's shared-memory carve-out (almost no L1)
+  // for its whole run - the attack step lost 5 ms of 157 with a trigger here, at the start or at the end of the kernel
+  // (profiles/r2_25_pdl_ab.txt).
+  pdl_wait();
 
   // The producer and the MMA issuer run as WHOLE warps with warp-uniform state and elect one lane only for the
   // asynchronous instructions themselves. Written as `if (lane == 0) { loop }` the same code compiled to ~130

@@ -25,6 +25,16 @@
 
 namespace leaf {
 
+// Programmatic dependent launch. Every GEMM, LayerNorm and attention launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization (engine.cu: launch_gemm, launch_pdl), and the non-GEMM kernels call
+// pdl_trigger() on entry: the GEMM that follows becomes resident while they drain, runs its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) and blocks in pdl_wait() until its predecessor has completed and its writes are visible.
+// Rule: nothing that a predecessor of the same per-layer chain writes may be read, and nothing may be written, before
+// pdl_wait() (the packed row count m_dev is written before the chain starts). Both are no-ops under an ordinary launch.
+// Worth 0.9 ms of the 13.0 ms K4 step (27 us kernels); neutral on the attack step (profiles/r2_25_pdl_ab.txt).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_UMMA_K = 16;

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "gemm_sm100.cuh"   // pdl_wait / pdl_trigger
+
 namespace leaf {
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -186,6 +188,8 @@ __global__ void __launch_bounds__(256) layernorm_bf16_kernel(const float* __rest
                                                             float eps, __nv_bfloat16* __restrict__ y,
                                                             const __nv_bfloat16* __restrict__ delta = nullptr,
                                                             __nv_bfloat16* __restrict__ y_lo = nullptr) {
+  pdl_wait();
+  pdl_trigger();     // the GEMM that follows sets itself up (barriers, TMEM, descriptors) while this grid runs
   const int rows = rows_dev ? min(*rows_dev, rows_max) : rows_max;
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
@@ -392,6 +396,8 @@ __global__ void __launch_bounds__(ATT_WARPS * 32, 4) attention_kernel(const __nv
                                                                        const int4* __restrict__ meta, int n_seq, int heads,
                                                                        int W, __nv_bfloat16* __restrict__ out,
                                                                        int last_only = 0) {
+  pdl_wait();
+  pdl_trigger();     // the GEMM that follows sets itself up (barriers, TMEM, descriptors) while this grid runs
   const int pair = blockIdx.x * ATT_WARPS + (threadIdx.x >> 5);
   if (pair >= n_seq * heads) return;
   const int seq = pair / heads, head = pair - seq * heads;

@@ -36,6 +36,7 @@ __global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat1
 // colsum[c] += sum_r du[r,c], the gradient of fc1's bias. A thread owns one column of a row band (coalesced across the CTA).
 __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dg, const __nv_bfloat16* __restrict__ u,
                                                       __nv_bfloat16* __restrict__ du, int R, int C, int act, float* __restrict__ colsum) {
+  pdl_trigger();     // the dgrad GEMM that follows may set itself up meanwhile (it reads du only after its pdl_wait)
   const int c = (blockIdx.x * 256 + threadIdx.x) * 4;     // four adjacent columns per thread: 16-byte dg loads, 8-byte u / du
   if (c >= C) return;
   const int band = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * band, r1 = min(r0 + band, R);
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
                                                            int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                            __nv_bfloat16* __restrict__ dx16 = nullptr,
                                                            float* __restrict__ dxsum = nullptr) {
+  pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   // dxsum != nullptr: dxsum[c] += sum over rows of the dx written here - the bias gradient of the Linear whose output
@@ -338,6 +340,7 @@ __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* 
                                                            int W, int T, __nv_bfloat16* __restrict__ dqkv,
                                                            float* __restrict__ db_q = nullptr, float* __restrict__ db_k = nullptr,
                                                            float* __restrict__ db_v = nullptr) {
+  pdl_trigger();
   extern __shared__ __align__(16) uint8_t attb_sm[];
   const int T16 = (T + 15) / 16 * 16, PP = T16 + 8;
   __nv_bfloat16* Qs = reinterpret_cast<__nv_bfloat16*>(attb_sm);
