@@ -113,6 +113,43 @@ def test_train_forward_with_host_lengths_does_not_change_anything():
     assert ((grads[0][1] - grads[1][1]).norm() / grads[0][1].norm()).item() < 1e-5
 
 
+def test_dependent_launch_changes_no_bit(monkeypatch):
+    """The per-layer chain is launched with programmatic dependent launch (a GEMM sets itself up under the tail of the LayerNorm /
+    attention kernel before it, csrc/gemm_sm100.cuh pdl_wait): the attack's features must equal, bit for bit, those of an engine
+    that launches every kernel ordinarily (LEAF_PDL=0), every time (a kernel that read its predecessor's output before
+    pdl_wait() would differ from run to run), and the training forward + backward must agree to the atomics' rounding."""
+    from leaf_b200 import synth
+    from leaf_b200.tower import LeafTextTower
+    sd = synth.random_tower_state_dict(synth.TOWERS["small"], seed=6, device="cuda")
+    monkeypatch.setenv("LEAF_PDL", "0")
+    plain = LeafTextTower({k: v.clone() for k, v in sd.items()}, heads=4).trainable()
+    monkeypatch.delenv("LEAF_PDL")
+    chained = LeafTextTower({k: v.clone() for k, v in sd.items()}, heads=4).trainable()
+    B, n = 24, 50
+    caps = synth.make_captions(B, seed=8)
+    rng = np.random.RandomState(2)
+    pos = torch.from_numpy(np.stack([rng.randint(0, 2 * len(S) + 1, size=n) for S in caps]).astype(np.int32)).cuda()
+    chr_ = torch.from_numpy(np.array(synth.V_DEFAULT, dtype=np.int32)[rng.randint(0, 96, size=(B, n))]).cuda()
+    outs = []
+    for tower in (plain, chained):
+        eng = tower.leaf_engine
+        d, o = eng.upload_captions(caps)
+        tok, ln, base = eng.expand_tokenize(d, o, B, n, pos, chr_)
+        outs.append(eng.encode_tokens(tok, ln, False, base, (B * n, n)))
+        for _ in range(5):
+            assert torch.equal(outs[-1], eng.encode_tokens(tok, ln, False, base, (B * n, n)))
+    assert torch.equal(outs[0], outs[1])
+    tok = plain.tokenizer(caps)
+    res = []
+    for tower in (plain, chained):
+        tower.zero_grad()
+        f = tower.encode_text(tok)
+        f.square().sum().backward()
+        res.append((f.detach().clone(), tower.flat_grads.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    assert ((res[0][1] - res[1][1]).norm() / res[0][1].norm()).item() < 1e-5
+
+
 def test_backward_hf_layout():
     from leaf_b200 import synth
     from leaf_b200.engine import LeafEngine
