@@ -239,7 +239,7 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
     tiles *= p.split_k;
     if (p.split_k > 1) epi = EPI_F32_SPLITK;
   }
-  TimedSpan span(e, (epi == EPI_F32_SPLITK) ? 4 + EPI_F32_RESIDUAL : (epi == EPI_F32_RESIDUAL && K > N) ? 8 : (epi == EPI_BF16 && K == N) ? 9 : 4 + epi, st);
+  TimedSpan span(e, (epi == EPI_F32_SPLITK) ? 4 + EPI_F32_RESIDUAL : (epi == EPI_BF16_ACTBWD) ? 4 + EPI_F32 : (epi == EPI_F32_RESIDUAL && K > N) ? 8 : (epi == EPI_BF16 && K == N) ? 9 : 4 + epi, st);
   const int pairs = static_cast<int>(tiles < pairs_cap ? tiles : pairs_cap);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * pairs);
@@ -259,6 +259,7 @@ static int launch_gemm(leaf_engine* e, const __nv_bfloat16* A, long a_rows, cons
     case EPI_F32_RESIDUAL: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, ta, tb, p)); break;
     case EPI_F32: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32>, ta, tb, p)); break;
     case EPI_F32_SPLITK: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_F32_SPLITK>, ta, tb, p)); break;
+    case EPI_BF16_ACTBWD: CK(cudaLaunchKernelEx(&cfg, gemm2_bf16_tn_kernel<EPI_BF16_ACTBWD>, ta, tb, p)); break;
     default: return fail(LEAF_ERR_INVALID, "unknown epilogue %d", epi);
   }
   e->launches++;
@@ -296,6 +297,7 @@ extern "C" int leaf_create(const leaf_cfg_t* cfg, leaf_handle_t* out) {
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_F32_SPLITK>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(gemm2_bf16_tn_kernel<EPI_BF16_ACTBWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT2_SMEM_BYTES));
   CK(cudaFuncSetAttribute(attention2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -966,15 +968,11 @@ extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* d
     const LayerW& w = e->lw[l];
     TrainLayer& a = t.L[l];
     // ================= MLP branch: x_next = x_mid + fc2(act(fc1(ln_2(x_mid)))) =================
-    if ((rc = dgrad(t.dx16, cap, w.fc2_w, t.dtmp, M, 4 * W, W))) return rc;                                 // dg [M,4W]
+    // du [M,4W] = (dx . W2[W,4W]) * act'(u), bf16, with fc1's bias gradient (its column sums): one GEMM, the activation
+    // backward is its epilogue (EPI_BF16_ACTBWD; a separate pass over an fp32 dg [M,4W] before)
+    if ((rc = launch_gemm(e, t.dx16, cap, w.fc2_w, nullptr, t.d16, 4 * W, M, 4 * W, W, EPI_BF16_ACTBWD, e->cfg.activation, nullptr, st,
+                          a.u, GEMM_B_MN, 0, nullptr, F(g.fc1_b)))) return rc;
     if (g.fc2_w && (rc = wgrad(t.dx16, 0, a.g, F(g.fc2_w), M, 4 * W, W))) return rc;
-    {
-      const int cb = (4 * W + 1023) / 1024;                  // 256 threads x 4 columns
-      int bands = (e->sm_count * 8 + cb - 1) / cb;
-      if (bands > M) bands = M;
-      act_bwd_kernel<<<dim3(cb, bands), 256, 0, st>>>(t.dtmp, a.u, t.d16, M, 4 * W, e->cfg.activation, F(g.fc1_b));   // du [M,4W] bf16 (+ fc1 bias grad)
-      e->launches++;
-    }
     if ((rc = dgrad(t.d16, cap, w.fc1_w, t.dtmp, M, W, 4 * W))) return rc;                                  // dh2 [M,W]
     if (g.fc1_w && (rc = wgrad(t.d16, 0, a.h2, F(g.fc1_w), M, W, 4 * W))) return rc;
     if ((rc = launch_layernorm_bwd(e, t.dtmp, a.x_mid, nullptr, M, p.ln2_w, t.dx, 1, F(g.ln2_w), F(g.ln2_b), scratch, st, t.dx16, F(g.out_b)))) return rc;

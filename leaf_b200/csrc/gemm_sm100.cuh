@@ -39,7 +39,8 @@ constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_UMMA_K = 16;
 
-enum { EPI_BF16 = 0, EPI_BF16_ACT = 1, EPI_F32_RESIDUAL = 2, EPI_F32 = 3, EPI_F32_SPLITK = 4 };   // 4: C += partial sums (red.global.add)
+enum { EPI_BF16 = 0, EPI_BF16_ACT = 1, EPI_F32_RESIDUAL = 2, EPI_F32 = 3, EPI_F32_SPLITK = 4,   // 4: C += partial sums (red.global.add)
+       EPI_BF16_ACTBWD = 5 };   // 5: C = bf16(acc * act'(U)), U = GemmParams::delta (bf16 [M, ldc]); C2 (fp32 [N], may be null) += column sums
 enum { ACT_GELU_ERF = 0, ACT_QUICK_GELU = 1 };
 
 struct GemmParams {
@@ -201,6 +202,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
 __device__ __forceinline__ float quick_gelu(float x) {                   // x sigmoid(1.702 x), transformer.py:33-36
   return x * fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));
 }
+// Derivatives for the backward's fused epilogue (EPI_BF16_ACTBWD): Phi(x) + x phi(x) with Phi as in gelu_erf above (|error|
+// <= 7e-5, the result is rounded to bf16), s + 1.702 x s (1 - s) for QuickGELU. 3 resp. 2 MUFU per element: exact erff / expf
+// forms would make the epilogue four times the tile's MMA time. tests/test_gpu_backward.py compares with autograd's.
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+  const float x2 = fminf(x * x, 36.0f);
+  const float r = fmaf(x2, fmaf(x2, 0.0011236976601259265f, -0.10762115607988151f), -2.299969046114191f);
+  const float cdf = fast_rcp(1.0f + fast_ex2(x * r));
+  const float pdf = 0.3989422804014327f * fast_ex2(-0.5f * 1.4426950408889634f * x2);
+  return fmaf(x, pdf, cdf);
+}
+__device__ __forceinline__ float quick_gelu_grad(float x) {
+  const float s = fast_rcp(1.0f + fast_ex2(-1.702f * 1.4426950408889634f * x));
+  return fmaf(1.702f * x * s, 1.0f - s, s);
+}
 // Fused epilogue of one 32-row x 32-column chunk of the accumulator. Each lane arrives with one ROW of the chunk
 // (v = raw fp32 bits from TMEM, tcgen05.ld 32x32b); storing that directly would touch 32 different 128-byte lines per
 // instruction (ncu r3: LSU wavefronts, not the tensor pipe, paced the K=1024 GEMMs). The chunk is bounced through a
@@ -282,7 +297,52 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
       for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
     }
   }
-  if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
+  if (EPI == EPI_BF16_ACTBWD) {
+    // du = dg * act'(u) (the backward's dgrad through fc2, fused with what was a separate activation-backward pass). The u tile comes in through the
+    // staging buffer (8 rows x 64 B per load instruction), each lane then reads its own row; rows past M are zeroed (their
+    // accumulators are whatever lay behind the operand) so that the column sums below - the gradient of fc1's bias - see
+    // exactly the values stored, rounded to bf16.
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int r = it * 8 + (lane >> 2);
+      uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+      if (col0 + c * 8 < p.N && row0 + r < M)
+        pk = *reinterpret_cast<const uint4*>(p.delta + static_cast<size_t>(row0 + r) * p.ldc + col0 + c * 8);
+      *reinterpret_cast<uint4*>(stage + r * 80 + c * 16) = pk;
+    }
+    __syncwarp();
+    const bool live = row0 + lane < M;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 pk = *reinterpret_cast<const uint4*>(stage + lane * 80 + q * 16);
+      const uint32_t w[4] = {pk.x, pk.y, pk.z, pk.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 u = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[k]));
+        const float g0 = p.act == ACT_QUICK_GELU ? quick_gelu_grad(u.x) : gelu_erf_grad(u.x);
+        const float g1 = p.act == ACT_QUICK_GELU ? quick_gelu_grad(u.y) : gelu_erf_grad(u.y);
+        const int j = 8 * q + 2 * k;
+        f[j] = live ? __bfloat162float(__float2bfloat16_rn(f[j] * g0)) : 0.f;
+        f[j + 1] = live ? __bfloat162float(__float2bfloat16_rn(f[j + 1] * g1)) : 0.f;
+      }
+    }
+    __syncwarp();                                 // every lane has read its row before the store reuses the buffer
+    store_bf16(p.C);
+    if (p.C2) {
+      // column sums over the 32 rows of the chunk: transpose-reduce by recursive halving (31 shuffles), lane j ends with column j
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = lane & off;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+          const float keep = up ? f[j + off] : f[j];
+          const float send = up ? f[j] : f[j + off];
+          f[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      if (col0 + lane < p.N) atomicAdd(reinterpret_cast<float*>(p.C2) + col0 + lane, f[0]);
+    }
+  } else if (EPI == EPI_BF16 || EPI == EPI_BF16_ACT) {
     store_bf16(p.C);
   } else {
 #pragma unroll

@@ -14,61 +14,8 @@
 
 namespace leaf {
 
-// ---- activation forward / backward (fc1 output u is saved pre-activation) -----------------------------------------
-__device__ __forceinline__ float act_fwd_exact(float u, int act) {
-  if (act == 1) return u / (1.f + expf(-1.702f * u));
-  return 0.5f * u * (1.f + erff(u * 0.70710678118654752440f));
-}
-__device__ __forceinline__ float act_grad_exact(float u, int act) {
-  if (act == 1) {
-    const float s = 1.f / (1.f + expf(-1.702f * u));
-    return s + 1.702f * u * s * (1.f - s);
-  }
-  const float cdf = 0.5f * (1.f + erff(u * 0.70710678118654752440f));
-  const float pdf = 0.3989422804014327f * expf(-0.5f * u * u);
-  return cdf + u * pdf;
-}
-__global__ void act_fwd_kernel(const __nv_bfloat16* __restrict__ u, __nv_bfloat16* __restrict__ g, size_t n, int act) {
-  for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    g[i] = __float2bfloat16_rn(act_fwd_exact(__bfloat162float(u[i]), act));
-}
-// du = dg * act'(u)   (dg fp32 [R,C] from the dgrad GEMM, du bf16 operand of the next GEMMs); colsum != nullptr:
-// colsum[c] += sum_r du[r,c], the gradient of fc1's bias. A thread owns one column of a row band (coalesced across the CTA).
-__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ dg, const __nv_bfloat16* __restrict__ u,
-                                                      __nv_bfloat16* __restrict__ du, int R, int C, int act, float* __restrict__ colsum) {
-  pdl_trigger();     // the dgrad GEMM that follows may set itself up meanwhile (it reads du only after its pdl_wait)
-  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;     // four adjacent columns per thread: 16-byte dg loads, 8-byte u / du
-  if (c >= C) return;
-  const int band = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * band, r1 = min(r0 + band, R);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  auto one = [&](const float4 d, const uint2 ub, size_t i) {
-    const float2 ua = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub.x));
-    const float2 uc = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ub.y));
-    const __nv_bfloat162 lo = __floats2bfloat162_rn(d.x * act_grad_exact(ua.x, act), d.y * act_grad_exact(ua.y, act));
-    const __nv_bfloat162 hi = __floats2bfloat162_rn(d.z * act_grad_exact(uc.x, act), d.w * act_grad_exact(uc.y, act));
-    uint2 pk;
-    pk.x = *reinterpret_cast<const uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<const uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(du + i) = pk;
-    const float2 fl = __bfloat1622float2(lo), fh = __bfloat1622float2(hi);
-    s0 += fl.x; s1 += fl.y; s2 += fh.x; s3 += fh.y;
-  };
-  int r = r0;
-  for (; r + 2 <= r1; r += 2) {                 // two independent rows in flight per thread
-    const size_t i0 = static_cast<size_t>(r) * C + c, i1 = i0 + C;
-    const float4 d0 = *reinterpret_cast<const float4*>(dg + i0), d1 = *reinterpret_cast<const float4*>(dg + i1);
-    const uint2 u0 = *reinterpret_cast<const uint2*>(u + i0), u1 = *reinterpret_cast<const uint2*>(u + i1);
-    one(d0, u0, i0);
-    one(d1, u1, i1);
-  }
-  if (r < r1) {
-    const size_t i = static_cast<size_t>(r) * C + c;
-    one(*reinterpret_cast<const float4*>(dg + i), *reinterpret_cast<const uint2*>(u + i), i);
-  }
-  if (colsum && r1 > r0) {
-    atomicAdd(colsum + c, s0); atomicAdd(colsum + c + 1, s1); atomicAdd(colsum + c + 2, s2); atomicAdd(colsum + c + 3, s3);
-  }
-}
+// The activation backward du = dg * act'(u) and fc1's bias gradient are the epilogue of the dgrad GEMM through fc2
+// (gemm_sm100.cuh, EPI_BF16_ACTBWD); the training forward's fc1 epilogue stores u and act(u) together.
 __global__ void scale_f32_kernel(float* __restrict__ g, size_t n, float s) {
   for (size_t i = (static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4; i + 3 < n; i += static_cast<size_t>(gridDim.x) * blockDim.x * 4) {
     float4 v = *reinterpret_cast<float4*>(g + i);
