@@ -708,7 +708,7 @@ extern "C" int leaf_test_attention(leaf_handle_t e, const void* qkv, const int32
 extern "C" int leaf_test_attention_bwd(leaf_handle_t e, const void* qkv, const void* o, const float* dout, const int32_t* meta,
                                        int32_t N, int32_t T, void* dqkv, void* stream) {
   if (!e || !qkv || !o || !dout || !meta || !dqkv || N <= 0 || T <= 0 || T > LEAF_CTX) return fail(LEAF_ERR_INVALID, "bad argument");
-  attention_bwd_kernel<<<dim3(N, e->cfg.heads), 32, attb_smem_bytes(T), static_cast<cudaStream_t>(stream)>>>(
+  attention_bwd_kernel<<<dim3(N, e->cfg.heads), ATTB_WARPS * 32, attb_smem_bytes(T), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(o), dout, reinterpret_cast<const int4*>(meta),
       e->cfg.width, T, static_cast<__nv_bfloat16*>(dqkv));
   e->launches++;
@@ -983,7 +983,7 @@ extern "C" int leaf_backward(leaf_handle_t e, int64_t generation, const float* d
       float* bq = p.in_proj_w ? F(g.in_proj_b) : F(g.q_b);
       float* bk = p.in_proj_w ? (g.in_proj_b ? F(g.in_proj_b) + W : nullptr) : F(g.k_b);
       float* bv = p.in_proj_w ? (g.in_proj_b ? F(g.in_proj_b) + 2 * W : nullptr) : F(g.v_b);
-      attention_bwd_kernel<<<dim3(N, e->cfg.heads), 32, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16, bq, bk, bv);
+      attention_bwd_kernel<<<dim3(N, e->cfg.heads), ATTB_WARPS * 32, attb_smem_bytes(t.T), st>>>(a.qkv, a.o, t.dtmp, t.meta, W, t.T, t.d16, bq, bk, bv);
     }
     e->launches++;
     CK(cudaGetLastError());

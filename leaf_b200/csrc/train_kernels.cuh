@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   }
 }
 
-// ---- causal attention backward on the tensor cores: one warp per (sequence, head) ------------------------------------------
+// ---- causal attention backward on the tensor cores: two warps per (sequence, head) ------------------------------------------
 // qkv bf16 [rows,3W], o bf16 [rows,W] (forward output), dout fp32 [rows,W] -> dqkv bf16 [rows,3W].
 //   P = softmax(scale Q K^T + causal), D_i = sum_d dO_id O_id, dP = dO V^T, dS = P o (dP - D),
 //   dV = P^T dO, dQ = scale dS K, dK = scale dS^T Q.
@@ -282,7 +282,10 @@ __device__ __forceinline__ void attb_colsum(const float (&acc)[8][4], float (&su
 
 // db_q / db_k / db_v (each may be null): [W] fp32, += the column sums of dQ / dK / dV (the in-projection's bias gradient;
 // the rows beyond a sequence's length are exactly zero in all three, so they do not disturb the sums)
-__global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
+// Two warps per (sequence, head): they split the staging rows, the query tiles of pass 1 and the key tiles of pass 2 (round
+// robin; the shared-memory footprint - what limits the CTAs per SM - is per item, so the second warp doubles the warps in flight).
+constexpr int ATTB_WARPS = 2;
+__global__ void __launch_bounds__(ATTB_WARPS * 32) attention_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ o,
                                                            const float* __restrict__ dout, const int4* __restrict__ meta,
                                                            int W, int T, __nv_bfloat16* __restrict__ dqkv,
                                                            float* __restrict__ db_q = nullptr, float* __restrict__ db_k = nullptr,
@@ -297,14 +300,14 @@ __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* 
   __nv_bfloat16* Ps = dOs + T16 * ATTB_PITCH;
   __nv_bfloat16* dSs = Ps + T16 * PP;
   float* Dv = reinterpret_cast<float*>(dSs + T16 * PP);
-  const int seq = blockIdx.x, head = blockIdx.y, lane = threadIdx.x;
+  const int seq = blockIdx.x, head = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int4 mt = meta[seq];
   const int row0 = mt.x, t = min(mt.y, T);              // training batches are packed without prefix sharing (p = 0)
   const int nt16 = (t + 15) / 16;                        // 16-row tiles of this sequence
   const size_t ld = static_cast<size_t>(3) * W;
   // ---- stage Q, K, V, dO (bf16) and D_i; 8 lanes per row, 16 bytes (8 elements) per lane ----
   const int sub = lane & 7;
-  for (int r = lane >> 3; r < nt16 * 16; r += 4) {
+  for (int r = threadIdx.x >> 3; r < nt16 * 16; r += 4 * ATTB_WARPS) {
     uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q, d = q;
     float dsum = 0.f;
     if (r < t) {
@@ -329,14 +332,14 @@ __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* 
     *reinterpret_cast<uint4*>(dOs + r * ATTB_PITCH + sub * 8) = d;
     if (sub == 0) Dv[r] = dsum;
   }
-  __syncwarp();
+  __syncthreads();
   const uint32_t sQ = smem_u32(Qs), sK = smem_u32(Ks), sV = smem_u32(Vs), sdO = smem_u32(dOs);
   const int g = lane >> 2, c = lane & 3;
   // ---- pass 1: per query tile S, dP, softmax, dS, dQ; P and dS to shared memory ----
   float sq[8][2], sk[8][2], sv[8][2];
 #pragma unroll
   for (int i = 0; i < 8; ++i) sq[i][0] = sq[i][1] = sk[i][0] = sk[i][1] = sv[i][0] = sv[i][1] = 0.f;
-  for (int qi = 0; qi < nt16; ++qi) {
+  for (int qi = warp; qi < nt16; qi += ATTB_WARPS) {
     float dq[8][4];
     switch (qi) {                                          // warp-uniform
       case 0: attb_query_tile<1>(sQ, sK, sV, sdO, Ps, dSs, Dv, PP, lane, dq); break;
@@ -354,14 +357,14 @@ __global__ void __launch_bounds__(32) attention_bwd_kernel(const __nv_bfloat16* 
       if (i1 < t) *reinterpret_cast<uint32_t*>(dst + static_cast<size_t>(row0 + i1) * ld) = pack_bf16x2(dq[n8][2], dq[n8][3]);
     }
   }
-  __syncwarp();
+  __syncthreads();
   // ---- pass 2: per key tile dV = sum_qi P^T dO, dK = sum_qi dS^T Q over the query tiles qi >= kj ----
   const uint32_t sP = smem_u32(Ps), sdS = smem_u32(dSs);
   // A operand from transposed storage: matrices (i 0-7, j 0-7), (i 0-7, j 8-15), (i 8-15, j 0-7), (i 8-15, j 8-15) of the [i][j] tile
   const int mi = lane >> 3;
   const uint32_t at_row = static_cast<uint32_t>((lane & 7) + 8 * (mi >> 1)), at_col = static_cast<uint32_t>(8 * (mi & 1));
   const uint32_t bt_off = static_cast<uint32_t>((((lane & 7) + 8 * ((lane >> 3) & 1)) * ATTB_PITCH + 8 * (lane >> 4)) * 2);
-  for (int kj = 0; kj < nt16; ++kj) {
+  for (int kj = warp; kj < nt16; kj += ATTB_WARPS) {
     float dv[8][4], dk[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
