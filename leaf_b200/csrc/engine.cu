@@ -69,6 +69,7 @@ struct TrainWs {
   std::vector<TrainLayer> L;
   float *x_out = nullptr, *dx = nullptr, *dtmp = nullptr, *scratch = nullptr;
   __nv_bfloat16 *pooled = nullptr, *d16 = nullptr, *dx16 = nullptr;
+  float* ln_stats = nullptr;         // (mean, rstd) per row, from the LayerNorm backward's row kernel to its column kernel
   int *tok = nullptr, *cu = nullptr, *eos_row = nullptr, *total_rows = nullptr, *pfx = nullptr, *own_len = nullptr;
   int4* meta = nullptr;
   std::vector<void*> allocs;
@@ -818,6 +819,7 @@ extern "C" int leaf_train_reserve(leaf_handle_t e, int32_t max_seqs) {
   if ((rc = tw_alloc(t, &t.pooled, (static_cast<size_t>(max_seqs) + 128) * W))) return rc;
   if ((rc = tw_alloc(t, &t.d16, rows * wide))) return rc;
   if ((rc = tw_alloc(t, &t.dx16, rows * W))) return rc;
+  if ((rc = tw_alloc(t, &t.ln_stats, rows * 2))) return rc;
   if ((rc = tw_alloc(t, &t.tok, static_cast<size_t>(max_seqs) * LEAF_CTX))) return rc;
   if ((rc = tw_alloc(t, &t.cu, static_cast<size_t>(max_seqs) + 1))) return rc;
   if ((rc = tw_alloc(t, &t.eos_row, static_cast<size_t>(max_seqs)))) return rc;
@@ -900,17 +902,24 @@ static int launch_layernorm_bwd(leaf_engine* e, const float* dy, const float* x,
   // frozen LayerNorm parameters (NULL grads) still need somewhere to add to: the scratch row pair
   if (!dgamma) dgamma = scratch;
   if (!dbeta) dbeta = scratch + W;
+  // rows kernel (dx, dx16, per-row mean / rstd) + column kernel (dgamma, dbeta, dxsum from the saved statistics): train_kernels.cuh
+  float2* stats = reinterpret_cast<float2*>(e->tw.ln_stats);
   int blocks = (rows + 7) / 8;
-  if (blocks > e->sm_count) blocks = e->sm_count;      // more CTAs lose to their extra atomics (2 x: +0.3 ms per backward, 4 x: +1.1 ms)
+  if (blocks > 2 * e->sm_count) blocks = 2 * e->sm_count;
   if (blocks < 1) blocks = 1;
-#define LNB_CASE(V) case V: layernorm_bwd_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gather, rows, W, gamma, e->cfg.ln_eps, dx, accumulate, dgamma, dbeta, dx16, dxsum); break;
+#define LNB_CASE(V) case V: layernorm_bwd_rows_kernel<V><<<blocks, 256, 0, st>>>(dy, x, gather, rows, W, gamma, e->cfg.ln_eps, dx, accumulate, dx16, stats); break;
   switch (W / 128) {
     LNB_CASE(1) LNB_CASE(2) LNB_CASE(3) LNB_CASE(4) LNB_CASE(5) LNB_CASE(6) LNB_CASE(7) LNB_CASE(8)
     LNB_CASE(9) LNB_CASE(10) LNB_CASE(11) LNB_CASE(12) LNB_CASE(13) LNB_CASE(14) LNB_CASE(15) LNB_CASE(16)
     default: return fail(LEAF_ERR_INVALID, "unsupported width %d", W);
   }
 #undef LNB_CASE
-  e->launches++;
+  const int cbx = (W + 255) / 256;
+  int bands = (2 * e->sm_count + cbx - 1) / cbx;
+  if (bands > (rows + 7) / 8) bands = (rows + 7) / 8;
+  if (bands < 1) bands = 1;
+  CK(launch_pdl(e, layernorm_bwd_cols_kernel, dim3(cbx, bands), dim3(256), st, dy, x, gather, stats, dx, rows, W, dgamma, dbeta, dxsum));
+  e->launches += 2;
   CK(cudaGetLastError());
   return LEAF_OK;
 }

@@ -36,33 +36,30 @@ template <>
 __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
 
 // ---- LayerNorm backward: dx[row] (+)= rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += dy*xhat; dbeta += dy
-// One warp per row. gather != nullptr: row r reads x[gather[r]] and WRITES dx[gather[r]] (final LN on the pooled rows).
+// gather != nullptr: row r reads x[gather[r]] and WRITES dx[gather[r]] (final LN on the pooled rows).
 // accumulate: dx += (residual branch) instead of dx = .
+// Two kernels. (1) A row kernel, one warp per row: dx, its bf16 copy (the A operand of the next dgrad GEMM) and the row's
+// (mean, rstd) saved to `stats`; no per-column accumulators, so two 8-warp CTAs fit an SM. (2) A column kernel in which a thread
+// owns four adjacent columns over a band of rows and rebuilds dy * xhat from the saved statistics (dy, x, dx are L2-resident at
+// K4's sizes): dgamma, dbeta and dxsum - the bias gradient of the Linear whose output gradient this dx is (fc2 of the layer below
+// for ln_1 / ln_final, out-proj for ln_2) - with 2 x SMs x 3 x 256 global atomics per launch. The single kernel this replaces
+// carried 3 x W/32 accumulators per lane through its row loop (255 registers, one CTA per SM) and ended in 3 W atomics per CTA:
+// 33 us per launch at 4 k rows against 24 for the pair (profiles/r2_33_lnb_split_ab.txt).
 template <int VPL>
-__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
-                                                           const int* __restrict__ gather, int rows, int W,
-                                                           const float* __restrict__ gamma, float eps, float* __restrict__ dx,
-                                                           int accumulate, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                           __nv_bfloat16* __restrict__ dx16 = nullptr,
-                                                           float* __restrict__ dxsum = nullptr) {
+__global__ void __launch_bounds__(256, VPL <= 10 ? 2 : 1) layernorm_bwd_rows_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                    const int* __restrict__ gather, int rows, int W,
+                                                                    const float* __restrict__ gamma, float eps, float* __restrict__ dx,
+                                                                    int accumulate, __nv_bfloat16* __restrict__ dx16,
+                                                                    float2* __restrict__ stats) {
   pdl_trigger();
   const int lane = threadIdx.x & 31;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
-  // dxsum != nullptr: dxsum[c] += sum over rows of the dx written here - the bias gradient of the Linear whose output
-  // gradient this dx is (fc2 of the layer below for ln_1 / ln_final, out-proj for ln_2), so no separate column-sum pass
-  float4 dg_acc[VPL], db_acc[VPL], ds_acc[VPL], g[VPL];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    dg_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    db_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    ds_acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    g[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
-  }
   const float invW = 1.f / static_cast<float>(W);
   for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < rows; r += warps_total) {
     const int xr = gather ? gather[r] : r;
     const float4* xin = reinterpret_cast<const float4*>(x + static_cast<size_t>(xr) * W);
     const float4* din = reinterpret_cast<const float4*>(dy + static_cast<size_t>(r) * W);
+    float4* out = reinterpret_cast<float4*>(dx + static_cast<size_t>(xr) * W);
     float4 xv[VPL], dv[VPL];
     float s = 0.f;
 #pragma unroll
@@ -79,20 +76,18 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       q += (xv[i].x * xv[i].x + xv[i].y * xv[i].y) + (xv[i].z * xv[i].z + xv[i].w * xv[i].w);
     }
     const float rstd = rsqrtf(warp_sum(q) * invW + eps);
+    if (lane == 0) stats[r] = make_float2(mean, rstd);
     float s1 = 0.f, s2 = 0.f;                 // sum(g*dy), sum(g*dy*xhat)
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
       xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;      // xhat
-      dg_acc[i].x += dv[i].x * xv[i].x; dg_acc[i].y += dv[i].y * xv[i].y;
-      dg_acc[i].z += dv[i].z * xv[i].z; dg_acc[i].w += dv[i].w * xv[i].w;
-      db_acc[i].x += dv[i].x; db_acc[i].y += dv[i].y; db_acc[i].z += dv[i].z; db_acc[i].w += dv[i].w;
-      dv[i].x *= g[i].x; dv[i].y *= g[i].y; dv[i].z *= g[i].z; dv[i].w *= g[i].w;   // g*dy
+      dv[i].x *= g.x; dv[i].y *= g.y; dv[i].z *= g.z; dv[i].w *= g.w;           // g*dy
       s1 += (dv[i].x + dv[i].y) + (dv[i].z + dv[i].w);
       s2 += (dv[i].x * xv[i].x + dv[i].y * xv[i].y) + (dv[i].z * xv[i].z + dv[i].w * xv[i].w);
     }
     s1 = warp_sum(s1) * invW;
     s2 = warp_sum(s2) * invW;
-    float4* out = reinterpret_cast<float4*>(dx + static_cast<size_t>(xr) * W);
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
       float4 o;
@@ -105,7 +100,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
         o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w;
       }
       out[lane + 32 * i] = o;
-      ds_acc[i].x += o.x; ds_acc[i].y += o.y; ds_acc[i].z += o.z; ds_acc[i].w += o.w;
       if (dx16) {                              // bf16 copy: the A operand of the next dgrad GEMM
         uint2 pk;
         pk.x = pack_bf16x2(o.x, o.y);
@@ -114,28 +108,56 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       }
     }
   }
-  // CTA-level reduction (warps take turns on a shared accumulator), then ONE atomic per column and CTA
-  __shared__ float red[3][VPL * 128];
-  for (int c = threadIdx.x; c < 3 * VPL * 128; c += blockDim.x) (&red[0][0])[c] = 0.f;
-  __syncthreads();
-  for (int w = 0; w < (blockDim.x >> 5); ++w) {
-    if ((threadIdx.x >> 5) == w) {
-#pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        float* a = &red[0][(lane + 32 * i) * 4];
-        float* b = &red[1][(lane + 32 * i) * 4];
-        float* d = &red[2][(lane + 32 * i) * 4];
-        a[0] += dg_acc[i].x; a[1] += dg_acc[i].y; a[2] += dg_acc[i].z; a[3] += dg_acc[i].w;
-        b[0] += db_acc[i].x; b[1] += db_acc[i].y; b[2] += db_acc[i].z; b[3] += db_acc[i].w;
-        d[0] += ds_acc[i].x; d[1] += ds_acc[i].y; d[2] += ds_acc[i].z; d[3] += ds_acc[i].w;
+}
+
+// dgamma[c] += sum_r dy[r,c] xhat[r,c], dbeta[c] += sum_r dy[r,c], dxsum[c] += sum_r dx[row(r),c] (dxsum may be null) over the
+// rows of this CTA's band. CTA = 64 column quads (256 columns) x 4 row phases; grid = (ceil(W / 256), bands).
+// Launched behind layernorm_bwd_rows_kernel with programmatic stream serialization: it reads that kernel's stats and dx.
+__global__ void __launch_bounds__(256) layernorm_bwd_cols_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                 const int* __restrict__ gather, const float2* __restrict__ stats,
+                                                                 const float* __restrict__ dx, int rows, int W,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 float* __restrict__ dxsum) {
+  pdl_wait();
+  pdl_trigger();
+  __shared__ float4 red[3][4][64];
+  const int quad = threadIdx.x & 63, ph = threadIdx.x >> 6;
+  const int c = blockIdx.x * 256 + quad * 4;
+  const int band = (rows + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * band, r1 = min(r0 + band, rows);
+  float4 ag = make_float4(0.f, 0.f, 0.f, 0.f), ab = ag, as = ag;
+  if (c < W) {
+    auto one = [&](int r) {
+      const int xr = gather ? gather[r] : r;
+      const float2 st = __ldg(stats + r);
+      const float4 d = *reinterpret_cast<const float4*>(dy + static_cast<size_t>(r) * W + c);
+      const float4 v = *reinterpret_cast<const float4*>(x + static_cast<size_t>(xr) * W + c);
+      ag.x += d.x * ((v.x - st.x) * st.y); ag.y += d.y * ((v.y - st.x) * st.y);
+      ag.z += d.z * ((v.z - st.x) * st.y); ag.w += d.w * ((v.w - st.x) * st.y);
+      ab.x += d.x; ab.y += d.y; ab.z += d.z; ab.w += d.w;
+      if (dxsum) {
+        const float4 o = *reinterpret_cast<const float4*>(dx + static_cast<size_t>(xr) * W + c);
+        as.x += o.x; as.y += o.y; as.z += o.z; as.w += o.w;
       }
-    }
-    __syncthreads();
+    };
+    int r = r0 + ph;
+    for (; r + 4 < r1; r += 8) { one(r); one(r + 4); }       // two independent rows in flight
+    if (r < r1) one(r);
   }
-  for (int c = threadIdx.x; c < W; c += blockDim.x) {
-    atomicAdd(dgamma + c, red[0][c]);
-    atomicAdd(dbeta + c, red[1][c]);
-    if (dxsum) atomicAdd(dxsum + c, red[2][c]);
+  red[0][ph][quad] = ag;
+  red[1][ph][quad] = ab;
+  red[2][ph][quad] = as;
+  __syncthreads();
+  // 768 sums per CTA (3 arrays x 256 columns): thread t takes column t of each array
+  const int col = blockIdx.x * 256 + threadIdx.x;
+  if (col < W && r1 > r0) {
+    const float* f = reinterpret_cast<const float*>(&red[0][0][0]);      // [array][phase][256 floats]
+    float* dst[3] = {dgamma, dbeta, dxsum};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (!dst[k]) continue;
+      const float* a = f + (k * 4) * 256 + threadIdx.x;
+      atomicAdd(dst[k] + col, (a[0] + a[256]) + (a[512] + a[768]));
+    }
   }
 }
 
